@@ -1,0 +1,196 @@
+/*
+ * sceneego_b200 -- C-ABI of the B200-native SceneEgo volumetric lifting stage.
+ *
+ * The reference (jianwang-mpi/SceneEgo) is pure Python: it has no FFI of its
+ * own, its boundary is the nn.Module `VoxelNetwork_depth` and four functions of
+ * `utils/op.py`.  Each entry point below replaces the torch / NumPy call site
+ * cited next to it; the Python mirror in `sceneego_b200/` binds them with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer; h_* is a HOST pointer;
+ *  - no call allocates, frees, synchronises or throws; `stream` is a
+ *    cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return value 0 = success, negative = SCENEEGO_E_* below;
+ *    `sceneego_last_error()` returns a thread-local message for the last failure;
+ *  - volumes are indexed (x, y, z) with flat voxel index x*V*V + y*V + z
+ *    (utils/op.py:212, network/voxel_net_depth.py:121-125).
+ */
+#ifndef SCENEEGO_B200_H
+#define SCENEEGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCENEEGO_ABI_VERSION 1
+
+enum {
+  SCENEEGO_OK = 0,
+  SCENEEGO_E_INVALID = -1,   /* bad argument (shape, alignment, null pointer)            */
+  SCENEEGO_E_CUDA = -2,      /* a CUDA runtime call or kernel launch failed               */
+  SCENEEGO_E_DOMAIN = -3,    /* "norm is zero!" -- a voxel centre on the optical axis
+                                (utils/fisheye/FishEyeCalibrated.py:177)                  */
+  SCENEEGO_E_UNSUPPORTED = -4
+};
+
+int sceneego_abi_version(void);
+const char* sceneego_last_error(void);
+
+/* Scaramuzza omnidirectional camera (utils/fisheye/FishEyeCalibrated.py:8-16,
+ * utils/fisheye/fisheye.calibration_05_08.json). Polynomials in ascending powers. */
+typedef struct sceneego_calib {
+  double cx, cy;       /* image centre, pixels                                         */
+  double c2w[7];       /* polynomialC2W: pixel radius -> z                             */
+  double w2c[11];      /* polynomialW2C: elevation angle -> image radius               */
+  int32_t width;       /* image plane of the tables, 1280                              */
+  int32_t height;      /* 1024                                                         */
+} sceneego_calib_t;
+
+/* ---- tables (built once) ------------------------------------------------- */
+
+/* Unit ray per pixel, fp64, replaces calculated_ray_direction_numpy
+ * (network/voxel_net_depth.py:147-155) + camera2world_ray
+ * (utils/fisheye/FishEyeCalibrated.py:36-51).  Same arithmetic order as NumPy
+ * (Horner without FMA, norm = sqrt((x^2+y^2)+z^2)) so the result is bit-identical.
+ * Layout written: d_ray[(y*width + x)*3 + c]  (ROW-major, matching a depth map;
+ * the reference's table is the same values in x-major order). */
+int sceneego_ray_table_f64(const sceneego_calib_t* calib, double* d_ray, void* stream);
+
+/* Voxel-centre projection, fp32, replaces build_coord_volume
+ * (network/voxel_net_depth.py:110-134) + world2camera_pytorch
+ * (utils/fisheye/FishEyeCalibrated.py:137-174) + get_grid_coord_proj_batch
+ * (utils/op.py:177-184).  Writes pixel coords d_px[N*2] and/or the normalised
+ * grid d_grid[N*2] (either may be NULL).  *d_status (int32, device, may be NULL)
+ * is set to 1 if any voxel has r == 0 (the reference raises). */
+int sceneego_project_voxels_f32(const sceneego_calib_t* calib, int volume_size, float cuboid_side,
+                                int heatmap_h, int heatmap_w, float* d_px, float* d_grid,
+                                int32_t* d_status, void* stream);
+
+/* ---- a1: process_features (network/voxel_net_depth.py:58-63) -------------- */
+
+/* 1x1 Conv2d + bias.  d_feat (B,Cin,H,W) f32 NCHW -> d_out (B,H,W,Cout) f32 channel-last.
+ * Cout must be 32, Cin a multiple of 32. */
+int sceneego_feature_conv1x1_f32(const float* d_feat, const float* d_weight, const float* d_bias,
+                                 float* d_out, int batch, int cin, int cout, int h, int w, void* stream);
+
+/* Nearest upsample to (up,up) + zero pad `pad` columns left/right, materialising the
+ * tensor the reference returns as output #2: d_in (B,h,w,C) channel-last ->
+ * d_out (B,C,up,up+2*pad) f32 NCHW. */
+int sceneego_features_upsample_pad_f32(const float* d_in, float* d_out, int batch, int c, int h, int w,
+                                       int up, int pad, void* stream);
+
+/* ---- a2/a3/a6: fused unprojection ----------------------------------------- */
+
+/* Activation layout consumed by the V2V kernels ("planar padded"):
+ * bf16, channel groups of 8, per group a linear array of voxel positions with
+ * zero guard columns/lines so that a conv tap is a constant position offset. */
+typedef struct sceneego_vol_layout {
+  int32_t side;          /* S: voxels per axis                                          */
+  int32_t pad;           /* zero positions after each z-line and y-lines after each plane */
+  int32_t pitch_y;       /* S + pad      positions per z-line                           */
+  int32_t pitch_x;       /* pitch_y^2    positions per x-plane                          */
+  int32_t guard;         /* zero positions in front of every frame                      */
+  int32_t frame_pitch;   /* guard + S*pitch_x                                           */
+  int64_t plane_stride;  /* positions per channel-group plane (all frames + slack)      */
+} sceneego_vol_layout_t;
+
+/* Fill a layout for (side, pad, batch); returns plane_stride (positions). */
+int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layout_t* out);
+
+/* Bilinear gather of the (virtually) x`scale`-upsampled, zero-padded feature map at the
+ * projected voxel centres.  Replaces Upsample+ConstantPad2d (voxel_net_depth.py:60-61)
+ * and F.grid_sample(bilinear, zeros, align_corners=True) (utils/op.py:209).
+ *   d_feat  (B,h,w,C) f32 channel-last, C == 32
+ *   d_grid  (N,2) f32 normalised coords in [-1,1] (table mode), or NULL to project the
+ *           voxel centres in-kernel through `calib` (fused Scaramuzza mode)
+ *   img_h/img_w : virtual image plane (1024 x 1280); scale = img_h / h; pad = (img_w-img_h)/2
+ *   d_out_f32   (B,C,V,V,V) f32 NCDHW or NULL
+ *   d_out_bf16  planar padded bf16 (layout `lay`), channels [0,C) or NULL */
+int sceneego_unproject_f32(const float* d_feat, const float* d_grid, const sceneego_calib_t* calib,
+                           int batch, int h, int w, int c, int volume_size, float cuboid_side,
+                           int img_h, int img_w, float* d_out_f32, void* d_out_bf16,
+                           const sceneego_vol_layout_t* lay, void* stream);
+
+/* ---- a4/a5: depth map -> occupancy grid ----------------------------------- */
+
+/* Replaces the per-frame host loop depth_map_to_voxel_numpy + point_cloud_to_voxel_numpy
+ * (network/voxel_net_depth.py:194-222, :251-257).  fp64 arithmetic without FMA contraction,
+ * round-half-even, bit-exact occupancy.
+ *   d_depth (B,h,w) f32; nearest-resized to img_h x img_h, padded to img_w
+ *   d_ray   (img_h*img_w*3) fp64 row-major from sceneego_ray_table_f64
+ *   d_occ_f32  (B,V,V,V) f32 {0,1}  -- must be zeroed by the caller -- or NULL
+ *   d_occ_bf16 planar padded bf16 volume (layout `lay`): channel `channel` set to 1.0
+ *              -- that channel must be zeroed by the caller -- or NULL */
+int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int h, int w, const double* d_ray,
+                                int img_h, int img_w, int volume_size, double cuboid_side,
+                                float* d_occ_f32, void* d_occ_bf16, const sceneego_vol_layout_t* lay,
+                                int channel, void* stream);
+
+/* Conversions between (B,C,S,S,S) f32 NCDHW and planar padded bf16 (for the
+ * scene_volumes= input path, voxel_net_depth.py:246-249, and for tests). */
+int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,
+                              const sceneego_vol_layout_t* lay, void* stream);
+int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_layout_t* lay, int batch, int c,
+                               float* d_out, void* stream);
+
+/* ---- a7: V2V encoder-decoder (network/v2v.py) ------------------------------ */
+
+enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2 };
+enum {
+  SCENEEGO_F_RELU = 1,         /* ReLU after bias (+ residual)                              */
+  SCENEEGO_F_RESIDUAL = 2,     /* add buffer `res` before the ReLU (Res3DBlock, v2v.py:40-43) */
+  SCENEEGO_F_ADD_AFTER = 4,    /* add buffer `res` after the ReLU (decoder skip, v2v.py:125-137) */
+  SCENEEGO_F_OUT_F32 = 8       /* write (B,cout_real,S,S,S) f32 NCDHW instead of planar bf16 */
+};
+
+/* One step of the V2V program.  Buffers are indices into the `buffers` array given
+ * to sceneego_v2v_run; each holds a planar padded bf16 volume with layout lay_*. */
+typedef struct sceneego_v2v_op {
+  int32_t type;        /* SCENEEGO_OP_*                                                    */
+  int32_t flags;       /* SCENEEGO_F_*                                                     */
+  int32_t ksize;       /* conv: 1, 3 or 7                                                  */
+  int32_t cin;         /* padded to a multiple of 16                                       */
+  int32_t cout;        /* padded to a multiple of 16                                       */
+  int32_t cout_real;   /* channels actually written (15 for the output layer)             */
+  int32_t src, dst, res;  /* buffer indices (res = -1 if unused)                           */
+  int32_t impl;        /* 0 = tcgen05 implicit GEMM, 1 = CUDA-core checker kernel          */
+  int64_t w_offset;    /* byte offset of the packed bf16 weights in the blob               */
+  int64_t b_offset;    /* byte offset of the fp32 bias (cout entries) in the blob          */
+  sceneego_vol_layout_t lay_src, lay_dst;
+} sceneego_v2v_op_t;
+
+/* Host-side fold + repack (replaces nn.BatchNorm3d eval, v2v.py:13,26,29,37,62, at load time).
+ *   h_weight: Conv3d (cout,cin,k,k,k) fp32, or ConvTranspose3d (cin,cout,2,2,2) if transposed
+ *   bn_*: NULL for no BatchNorm.  Output: bf16 [tap][cin_pad/8][cout_pad][8] and fp32 bias. */
+int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
+                           const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
+                           double eps, int cout, int cin, int ksize, int transposed, int cout_pad,
+                           int cin_pad, uint16_t* h_w_out, float* h_b_out);
+
+/* Execute `n_ops` steps on `batch` frames.  d_blob: packed weights + biases. */
+int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,
+                     int batch, void* stream);
+
+/* Number of kernels the last sceneego_v2v_run on this thread launched. */
+int sceneego_v2v_last_launch_count(void);
+
+/* ---- a8: soft-argmax (utils/op.py:83-96) ----------------------------------- */
+
+/* d_logits (B,J,V,V,V) f32; multiplier applied first (voxel_net_depth.py:271).
+ * Coordinates: d_axis (3,V) f32 per-axis voxel-centre table (regular grid), or
+ * d_coords (N,3) f32 arbitrary (exactly one non-NULL).  softmax=0 -> ReLU, unnormalised.
+ *   d_keypoints (B,J,3) f32;  d_volumes_out (B,J,V,V,V) f32 or NULL
+ *   d_workspace: at least sceneego_softargmax_workspace_bytes(B,J,V) bytes */
+size_t sceneego_softargmax_workspace_bytes(int batch, int joints, int volume_size);
+int sceneego_softargmax3d_f32(const float* d_logits, int batch, int joints, int volume_size,
+                              float multiplier, int softmax, const float* d_axis, const float* d_coords,
+                              float* d_keypoints, float* d_volumes_out, void* d_workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCENEEGO_B200_H */

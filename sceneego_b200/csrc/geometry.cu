@@ -1,0 +1,435 @@
+// Camera tables, depth-map voxelisation (a4/a5) and fused unprojection (a1-a3, a6).
+// All kernels here are HBM-bound byte/float work: coalesced, vectorised, no tensor cores.
+#include "common.cuh"
+
+namespace sceneego {
+
+// ---------------------------------------------------------------------------
+// a4: unit ray per pixel, fp64, bit-identical to the NumPy reference
+// (utils/fisheye/FishEyeCalibrated.py:42-50).  No FMA contraction anywhere.
+// ---------------------------------------------------------------------------
+__global__ void ray_table_kernel(CalibDev cal, double* __restrict__ ray) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= cal.width) return;
+  const double xc = __dsub_rn((double)x, cal.cx);
+  const double yc = __dsub_rn((double)y, cal.cy);
+  const double r2 = __dadd_rn(__dmul_rn(xc, xc), __dmul_rn(yc, yc));
+  const double d = sqrt(r2);
+  double z = 0.0;  // np.polyval: y = y*x + c, highest power first
+#pragma unroll
+  for (int i = 6; i >= 0; --i) z = __dadd_rn(__dmul_rn(z, d), cal.c2w[i]);
+  const double nz = -z;
+  const double norm = sqrt(__dadd_rn(r2, __dmul_rn(nz, nz)));
+  double* o = ray + ((size_t)y * cal.width + x) * 3;
+  o[0] = __ddiv_rn(xc, norm);
+  o[1] = __ddiv_rn(yc, norm);
+  o[2] = __ddiv_rn(nz, norm);
+}
+
+// ---------------------------------------------------------------------------
+// a3: voxel centre -> pixel (Scaramuzza W2C polynomial), fp32 like the reference
+// (utils/fisheye/FishEyeCalibrated.py:147-174).  Shared by the table builder and
+// by the fused gather kernel.
+// ---------------------------------------------------------------------------
+struct W2CF32 {
+  float a[11];
+  float cx, cy;
+};
+
+__device__ __forceinline__ bool project_voxel(const W2CF32& k, float X, float Y, float Z, float& px, float& py) {
+  const float z = __fmul_rn(Z, -1.0f);
+  const float r = sqrtf(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)));
+  if (r == 0.0f) { px = k.cx; py = k.cy; return false; }
+  const float theta = atanf(__fdiv_rn(z, r));
+  const float inv = __fdiv_rn(1.0f, r);
+  float rho = k.a[0];
+  float t = 1.0f;
+#pragma unroll
+  for (int i = 1; i < 11; ++i) {
+    t = __fmul_rn(t, theta);
+    rho = __fadd_rn(rho, __fmul_rn(t, k.a[i]));
+  }
+  px = __fadd_rn(__fmul_rn(__fmul_rn(X, inv), rho), k.cx);
+  py = __fadd_rn(__fmul_rn(__fmul_rn(Y, inv), rho), k.cy);
+  return true;
+}
+
+__device__ __forceinline__ void normalise_px(float px, float py, int hm_h, int hm_w, float& gx, float& gy) {
+  // utils/op.py:179-180: g = 2 * (p / [W,H] - 0.5)
+  gx = __fmul_rn(2.0f, __fsub_rn(__fdiv_rn(px, (float)hm_w), 0.5f));
+  gy = __fmul_rn(2.0f, __fsub_rn(__fdiv_rn(py, (float)hm_h), 0.5f));
+}
+
+static W2CF32 make_w2c(const sceneego_calib_t* c) {
+  W2CF32 k;
+  for (int i = 0; i < 11; ++i) k.a[i] = (float)c->w2c[i];
+  k.cx = (float)c->cx;
+  k.cy = (float)c->cy;
+  return k;
+}
+
+__global__ void project_voxels_kernel(W2CF32 k, int V, float lo, float step, int hm_h, int hm_w,
+                                      float* __restrict__ px_out, float* __restrict__ grid_out,
+                                      int* __restrict__ status) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= V * V * V) return;
+  const int z = n % V, y = (n / V) % V, x = n / (V * V);
+  float px, py;
+  const bool ok = project_voxel(k, voxel_coord(lo, step, x), voxel_coord(lo, step, y),
+                                voxel_coord(0.0f, step, z), px, py);
+  if (!ok && status) atomicExch(status, 1);
+  if (px_out) { px_out[2 * n] = px; px_out[2 * n + 1] = py; }
+  if (grid_out) {
+    float gx, gy;
+    normalise_px(px, py, hm_h, hm_w, gx, gy);
+    grid_out[2 * n] = gx;
+    grid_out[2 * n + 1] = gy;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// a1: 1x1 Conv2d 256 -> 32 (+bias), NCHW f32 in, channel-last f32 out.
+// One CTA = 64 pixels x 32 output channels; K streamed through smem in chunks of 32.
+// ---------------------------------------------------------------------------
+constexpr int FC_PIX = 64, FC_KC = 32, FC_CO = 32;
+
+__global__ void __launch_bounds__(256) feature_conv1x1_kernel(const float* __restrict__ feat,
+                                                             const float* __restrict__ weight,
+                                                             const float* __restrict__ bias,
+                                                             float* __restrict__ out, int cin, int hw) {
+  __shared__ float s_in[FC_KC][FC_PIX];      // [k][pixel]
+  __shared__ float s_w[FC_KC][FC_CO + 1];    // [k][co]
+  const int b = blockIdx.y;
+  const int pix0 = blockIdx.x * FC_PIX;
+  const int tid = threadIdx.x;
+  const int co = tid & 31;        // lane -> output channel (channel-last store is coalesced)
+  const int pg = tid >> 5;        // 8 pixel groups of 8 pixels
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const float* fb = feat + (size_t)b * cin * hw;
+  for (int k0 = 0; k0 < cin; k0 += FC_KC) {
+    for (int i = tid; i < FC_KC * FC_PIX; i += 256) {
+      const int kk = i / FC_PIX, p = i % FC_PIX;
+      s_in[kk][p] = (pix0 + p < hw) ? fb[(size_t)(k0 + kk) * hw + pix0 + p] : 0.f;
+    }
+    for (int i = tid; i < FC_KC * FC_CO; i += 256) {
+      const int c = i / FC_KC, kk = i % FC_KC;
+      s_w[kk][c] = weight[(size_t)c * cin + k0 + kk];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < FC_KC; ++kk) {
+      const float w = s_w[kk][co];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(s_in[kk][pg * 8 + i], w, acc[i]);
+    }
+    __syncthreads();
+  }
+  const float bv = bias[co];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = pix0 + pg * 8 + i;
+    if (p < hw) out[((size_t)b * hw + p) * FC_CO + co] = acc[i] + bv;
+  }
+}
+
+// Output #2 of the reference forward: nearest upsample + pad, materialised only on request.
+__global__ void upsample_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int c, int h, int w,
+                                    int up, int pad) {
+  const int W = up + 2 * pad;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int bc = blockIdx.z;
+  if (x4 >= W) return;
+  const int b = bc / c, ch = bc % c;
+  const int sy = (int)(((long long)y * h) / up);
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x4 + i - pad;
+    v[i] = (x >= 0 && x < up) ? in[(((size_t)b * h + sy) * w + (int)(((long long)x * w) / up)) * c + ch] : 0.f;
+  }
+  *reinterpret_cast<float4*>(out + ((size_t)bc * up + y) * W + x4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ---------------------------------------------------------------------------
+// a2/a3/a6: fused (projection +) bilinear gather.
+// One thread = one voxel, all 32 channels.  The x16-upsampled, zero-padded image of the
+// reference is never materialised: tap (X,Y) of the virtual img_h x img_w plane maps to
+// source cell (Y*h/img_h, (X-pad)*w/up).  Channel-last f32 source rows are read as float4
+// (8 x 16 B per tap); consecutive voxels (z fastest) project to neighbouring pixels, so
+// the 512 KB per-frame source stays in L1/L2.  Stores: f32 NCDHW (128 B per warp per
+// channel) and/or bf16 planar padded (512 B per warp per channel group).
+// ---------------------------------------------------------------------------
+template <bool kProject>
+__global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict__ feat, const float* __restrict__ grid,
+                                                       W2CF32 cam, int h, int w, int V, float lo, float step,
+                                                       int img_h, int img_w, float* __restrict__ out_f32,
+                                                       __nv_bfloat16* __restrict__ out_bf16,
+                                                       sceneego_vol_layout_t lay) {
+  constexpr int C = 32;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  const int N = V * V * V;
+  if (n >= N) return;
+  const int vz = n % V, vy = (n / V) % V, vx = n / (V * V);
+  float gx, gy;
+  if (kProject) {
+    float px, py;
+    project_voxel(cam, voxel_coord(lo, step, vx), voxel_coord(lo, step, vy), voxel_coord(0.0f, step, vz), px, py);
+    normalise_px(px, py, img_h, img_w, gx, gy);
+  } else {
+    const float2 g = reinterpret_cast<const float2*>(grid)[n];
+    gx = g.x; gy = g.y;
+  }
+  // ATen grid_sampler_2d, align_corners=True: ix = ((g+1)/2)*(W-1)
+  const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(img_w - 1));
+  const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(img_h - 1));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float wx1 = ix - x0f, wy1 = iy - y0f;
+  const float wx0 = (x0f + 1.0f) - ix, wy0 = (y0f + 1.0f) - iy;
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int pad = (img_w - img_h) / 2;
+
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  const float* fb = feat + (size_t)b * h * w * C;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int X = x0 + (t & 1), Y = y0 + (t >> 1);
+    const float wt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+    const bool inb = (X >= 0) && (X < img_w) && (Y >= 0) && (Y < img_h);   // zeros padding
+    const int xs = X - pad;
+    if (inb && xs >= 0 && xs < img_h) {                                    // outside: ConstantPad2d zeros
+      const int sy = (int)(((long long)Y * h) / img_h);
+      const int sx = (int)(((long long)xs * w) / img_h);
+      const float4* src = reinterpret_cast<const float4*>(fb + ((size_t)sy * w + sx) * C);
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        const float4 v = __ldg(src + q);
+        acc[4 * q + 0] = fmaf(v.x, wt, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v.y, wt, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v.z, wt, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v.w, wt, acc[4 * q + 3]);
+      }
+    }
+  }
+  if (out_f32) {
+    float* o = out_f32 + (size_t)b * C * N + n;
+#pragma unroll
+    for (int c = 0; c < C; ++c) __stcs(o + (size_t)c * N, acc[c]);
+  }
+  if (out_bf16) {
+    const int64_t pos = vol_pos(lay, b, vx, vy, vz);
+#pragma unroll
+    for (int g = 0; g < C / 8; ++g) {
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pk[q] = __floats2bfloat162_rn(acc[8 * g + 2 * q], acc[8 * g + 2 * q + 1]);
+      *reinterpret_cast<uint4*>(out_bf16 + ((int64_t)g * lay.plane_stride + pos) * 8) =
+          *reinterpret_cast<const uint4*>(pk);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// a5: back-project every pixel of the (nearest-resized, padded) depth map and scatter
+// occupancy.  fp64, round-half-even, exactly the NumPy order of
+// network/voxel_net_depth.py:199-217.  One thread = one pixel of the img_h x img_w plane,
+// row-major, so depth, ray table (24 B / pixel, L2 resident across frames) and the
+// zero-padding test are all coalesced.  The scatter is a benign same-value race.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__ depth, int h, int w,
+                                                      const double* __restrict__ ray, int img_h, int img_w, int V,
+                                                      double side, float* __restrict__ occ_f32,
+                                                      __nv_bfloat16* __restrict__ occ_bf16,
+                                                      sceneego_vol_layout_t lay, int channel) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (X >= img_w) return;
+  const int pad = (img_w - img_h) / 2;
+  const int xs = X - pad;
+  float dv = 0.f;
+  if (xs >= 0 && xs < img_h) {
+    // cv2.resize(INTER_NEAREST): src = min(floor(dst * in / out), in - 1)
+    int sy = (int)(((long long)Y * h) / img_h);
+    int sx = (int)(((long long)xs * w) / img_h);
+    sy = sy < h - 1 ? sy : h - 1;
+    sx = sx < w - 1 ? sx : w - 1;
+    dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
+  }
+  const double d = (double)dv;
+  const double* r = ray + ((size_t)Y * img_w + X) * 3;
+  const double half = side / 2;             // cuboid_side / 2
+  const double Vd = (double)V;
+  const double qx = rint(__ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(r[0], d), half), Vd), side));
+  const double qy = rint(__ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(r[1], d), half), Vd), side));
+  const double qz = rint(__ddiv_rn(__dmul_rn(__dmul_rn(r[2], d), Vd), side));
+  const double hi = (double)(V - 1);
+  if (qx >= 0.0 && qx <= hi && qy >= 0.0 && qy <= hi && qz >= 0.0 && qz <= hi) {
+    const int ix = (int)qx, iy = (int)qy, iz = (int)qz;
+    if (occ_f32) occ_f32[(((size_t)b * V + ix) * V + iy) * V + iz] = 1.0f;
+    if (occ_bf16) {
+      const int64_t pos = vol_pos(lay, b, ix, iy, iz);
+      occ_bf16[((int64_t)(channel >> 3) * lay.plane_stride + pos) * 8 + (channel & 7)] = __float2bfloat16(1.0f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// layout conversions (scene_volumes= input path; tests)
+// ---------------------------------------------------------------------------
+__global__ void pack_volume_kernel(const float* __restrict__ in, int c, int c_offset, __nv_bfloat16* __restrict__ out,
+                                   sceneego_vol_layout_t lay) {
+  const int S = lay.side;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= S * S * S) return;
+  const int z = n % S, y = (n / S) % S, x = n / (S * S);
+  const int64_t pos = vol_pos(lay, b, x, y, z);
+  for (int ch = 0; ch < c; ++ch) {
+    const int oc = ch + c_offset;
+    out[((int64_t)(oc >> 3) * lay.plane_stride + pos) * 8 + (oc & 7)] =
+        __float2bfloat16(in[((size_t)b * c + ch) * S * S * S + n]);
+  }
+}
+
+__global__ void unpack_volume_kernel(const __nv_bfloat16* __restrict__ in, sceneego_vol_layout_t lay, int c,
+                                     float* __restrict__ out) {
+  const int S = lay.side;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= S * S * S) return;
+  const int z = n % S, y = (n / S) % S, x = n / (S * S);
+  const int64_t pos = vol_pos(lay, b, x, y, z);
+  for (int ch = 0; ch < c; ++ch)
+    out[((size_t)b * c + ch) * S * S * S + n] =
+        __bfloat162float(in[((int64_t)(ch >> 3) * lay.plane_stride + pos) * 8 + (ch & 7)]);
+}
+
+}  // namespace sceneego
+
+using namespace sceneego;
+
+extern "C" int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layout_t* out) {
+  if (side <= 0 || pad < 0 || batch <= 0 || !out) return SCENEEGO_E_INVALID;
+  sceneego_vol_layout_t L;
+  L.side = side;
+  L.pad = pad;
+  L.pitch_y = side + pad;
+  L.pitch_x = L.pitch_y * L.pitch_y;
+  // guard: largest tap offset of a (2*pad+1)^3 stencil, rounded up to 8 positions (128 B)
+  const int g = pad * (L.pitch_x + L.pitch_y + 1);
+  L.guard = (g + 7) / 8 * 8;
+  L.frame_pitch = ((L.guard + side * L.pitch_x) + 7) / 8 * 8;
+  // slack after the last frame: one trailing guard + the widest CTA work item (1024 positions)
+  L.plane_stride = (int64_t)batch * L.frame_pitch + L.guard + 1024 + 8;
+  *out = L;
+  return L.plane_stride;
+}
+
+extern "C" int sceneego_ray_table_f64(const sceneego_calib_t* calib, double* d_ray, void* stream) {
+  SE_REQUIRE(calib && d_ray, "ray_table: null argument");
+  SE_REQUIRE(calib->width > 0 && calib->height > 0, "ray_table: bad image size");
+  dim3 grid((calib->width + 255) / 256, calib->height);
+  ray_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(to_dev(calib), d_ray);
+  SE_CUDA_LAUNCH_CHECK("ray_table");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_project_voxels_f32(const sceneego_calib_t* calib, int V, float side, int hm_h, int hm_w,
+                                           float* d_px, float* d_grid, int32_t* d_status, void* stream) {
+  SE_REQUIRE(calib && (d_px || d_grid), "project_voxels: null argument");
+  SE_REQUIRE(V >= 2 && V <= 512, "project_voxels: volume_size out of range");
+  const float step = (float)((double)side / (V - 1));
+  const float lo = (float)(-(double)side / 2);
+  const int N = V * V * V;
+  project_voxels_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_w2c(calib), V, lo, step, hm_h, hm_w,
+                                                                           d_px, d_grid, d_status);
+  SE_CUDA_LAUNCH_CHECK("project_voxels");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_feature_conv1x1_f32(const float* d_feat, const float* d_weight, const float* d_bias,
+                                            float* d_out, int batch, int cin, int cout, int h, int w, void* stream) {
+  SE_REQUIRE(d_feat && d_weight && d_bias && d_out, "feature_conv1x1: null argument");
+  SE_REQUIRE(cout == FC_CO && cin % FC_KC == 0 && batch > 0, "feature_conv1x1: need cout == 32, cin %% 32 == 0");
+  dim3 grid((h * w + FC_PIX - 1) / FC_PIX, batch);
+  feature_conv1x1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feat, d_weight, d_bias, d_out, cin, h * w);
+  SE_CUDA_LAUNCH_CHECK("feature_conv1x1");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_features_upsample_pad_f32(const float* d_in, float* d_out, int batch, int c, int h, int w,
+                                                  int up, int pad, void* stream) {
+  SE_REQUIRE(d_in && d_out && batch > 0, "features_upsample_pad: null argument");
+  SE_REQUIRE((up + 2 * pad) % 4 == 0, "features_upsample_pad: output width must be a multiple of 4");
+  SE_REQUIRE((long long)batch * c <= 65535, "features_upsample_pad: batch*c too large for one launch");
+  dim3 grid(((up + 2 * pad) / 4 + 127) / 128, up, batch * c);
+  upsample_pad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_in, d_out, c, h, w, up, pad);
+  SE_CUDA_LAUNCH_CHECK("features_upsample_pad");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, const sceneego_calib_t* calib,
+                                      int batch, int h, int w, int c, int V, float side, int img_h, int img_w,
+                                      float* d_out_f32, void* d_out_bf16, const sceneego_vol_layout_t* lay,
+                                      void* stream) {
+  SE_REQUIRE(d_feat && (d_grid || calib) && (d_out_f32 || d_out_bf16), "unproject: null argument");
+  SE_REQUIRE(c == 32, "unproject: 32 feature channels expected (process_features output)");
+  SE_REQUIRE(!d_out_bf16 || (lay && lay->side == V), "unproject: bf16 output needs a matching layout");
+  SE_REQUIRE(batch > 0 && batch <= 65535 && img_w >= img_h, "unproject: bad batch / image plane");
+  const int N = V * V * V;
+  dim3 grid((N + 127) / 128, batch);
+  sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
+  const float step = (float)((double)side / (V - 1));
+  const float lo = (float)(-(double)side / 2);
+  W2CF32 cam = calib ? make_w2c(calib) : W2CF32{};
+  if (d_grid)
+    unproject_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, d_grid, cam, h, w, V, lo, step, img_h,
+                                                                    img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L);
+  else
+    unproject_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, nullptr, cam, h, w, V, lo, step, img_h,
+                                                                   img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L);
+  SE_CUDA_LAUNCH_CHECK("unproject");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int h, int w, const double* d_ray,
+                                           int img_h, int img_w, int V, double side, float* d_occ_f32,
+                                           void* d_occ_bf16, const sceneego_vol_layout_t* lay, int channel,
+                                           void* stream) {
+  SE_REQUIRE(d_depth && d_ray && (d_occ_f32 || d_occ_bf16), "voxelize: null argument");
+  SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && img_w >= img_h, "voxelize: bad shape");
+  SE_REQUIRE(!d_occ_bf16 || (lay && lay->side == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
+  dim3 grid((img_w + 255) / 256, img_h, batch);
+  sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
+  voxelize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, d_occ_f32,
+                                                          (__nv_bfloat16*)d_occ_bf16, L, channel);
+  SE_CUDA_LAUNCH_CHECK("voxelize");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,
+                                         const sceneego_vol_layout_t* lay, void* stream) {
+  SE_REQUIRE(d_in && d_out && lay && batch > 0 && batch <= 65535, "pack_volume: bad argument");
+  const int N = lay->side * lay->side * lay->side;
+  pack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>(d_in, c, c_offset,
+                                                                                      (__nv_bfloat16*)d_out, *lay);
+  SE_CUDA_LAUNCH_CHECK("pack_volume");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_layout_t* lay, int batch, int c,
+                                          float* d_out, void* stream) {
+  SE_REQUIRE(d_in && d_out && lay && batch > 0 && batch <= 65535, "unpack_volume: bad argument");
+  const int N = lay->side * lay->side * lay->side;
+  unpack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_in,
+                                                                                        *lay, c, d_out);
+  SE_CUDA_LAUNCH_CHECK("unpack_volume");
+  return SCENEEGO_OK;
+}
