@@ -70,6 +70,12 @@ int sceneego_project_voxels_f32(const sceneego_calib_t* calib, int volume_size, 
                                 int heatmap_h, int heatmap_w, float* d_px, float* d_grid,
                                 int32_t* d_status, void* stream);
 
+/* Arbitrary points: d_points (N,3) f32 -> d_px (N,2) f32; replaces
+ * FishEyeCameraCalibrated.world2camera_pytorch (utils/fisheye/FishEyeCalibrated.py:137-187,
+ * normalize=False) as reached through utils/multiview.py:128-130 and utils/op.py:98-116. */
+int sceneego_world2camera_f32(const sceneego_calib_t* calib, const float* d_points, int n_points,
+                              float* d_px, int32_t* d_status, void* stream);
+
 /* ---- a1: process_features (network/voxel_net_depth.py:58-63) -------------- */
 
 /* 1x1 Conv2d + bias.  d_feat (B,Cin,H,W) f32 NCHW -> d_out (B,H,W,Cout) f32 channel-last.
@@ -109,11 +115,21 @@ int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layo
  *           voxel centres in-kernel through `calib` (fused Scaramuzza mode)
  *   img_h/img_w : virtual image plane (1024 x 1280); scale = img_h / h; pad = (img_w-img_h)/2
  *   d_out_f32   (B,C,V,V,V) f32 NCDHW or NULL
- *   d_out_bf16  planar padded bf16 (layout `lay`), channels [0,C) or NULL */
+ *   d_out_bf16  planar padded bf16 (layout `lay`), channels [0,C) or NULL
+ *   extra_zero_planes: 8-channel planes after the features cleared at every voxel (the scene
+ *           channel of the 33-channel V2V input, torch.cat at voxel_net_depth.py:262) */
 int sceneego_unproject_f32(const float* d_feat, const float* d_grid, const sceneego_calib_t* calib,
                            int batch, int h, int w, int c, int volume_size, float cuboid_side,
                            int img_h, int img_w, float* d_out_f32, void* d_out_bf16,
-                           const sceneego_vol_layout_t* lay, void* stream);
+                           const sceneego_vol_layout_t* lay, int extra_zero_planes, void* stream);
+
+/* Generic bilinear gather with the reference op's own signature: replaces
+ * F.grid_sample(heatmaps, grid, align_corners=True) at utils/op.py:209 (and :163) on a
+ * materialised image.  d_img (B,C,H,W) f32 NCHW; d_grid (N,2) normalised coords, frame b
+ * reads d_grid + b*grid_batch_stride floats (0 = one grid shared by the batch);
+ * d_out (B,C,N) f32. */
+int sceneego_grid_sample_f32(const float* d_img, const float* d_grid, int64_t grid_batch_stride, int batch,
+                             int c, int h, int w, int n_points, float* d_out, void* stream);
 
 /* ---- a4/a5: depth map -> occupancy grid ----------------------------------- */
 

@@ -1,0 +1,227 @@
+"""ctypes binding of libsceneego_b200.so (the C-ABI of include/sceneego_b200.h).
+
+There is NO fallback: if the CUDA library cannot be loaded, or a tensor is not
+on a CUDA device, every op raises.  PyTorch is used only for device memory and
+streams; all compute goes through the extern "C" entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsceneego_b200.so")
+
+SYMBOLS = [
+    "sceneego_abi_version", "sceneego_last_error", "sceneego_ray_table_f64", "sceneego_project_voxels_f32",
+    "sceneego_feature_conv1x1_f32", "sceneego_features_upsample_pad_f32", "sceneego_vol_layout_make",
+    "sceneego_unproject_f32", "sceneego_voxelize_depth_f64", "sceneego_pack_volume_bf16",
+    "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run",
+    "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
+    "sceneego_world2camera_f32", "sceneego_grid_sample_f32",
+]
+
+
+class Calib(C.Structure):
+    _fields_ = [("cx", C.c_double), ("cy", C.c_double), ("c2w", C.c_double * 7), ("w2c", C.c_double * 11),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class VolLayout(C.Structure):
+    _fields_ = [("side", C.c_int32), ("pad", C.c_int32), ("pitch_y", C.c_int32), ("pitch_x", C.c_int32),
+                ("guard", C.c_int32), ("frame_pitch", C.c_int32), ("plane_stride", C.c_int64)]
+
+
+class V2VOp(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_int32), ("ksize", C.c_int32), ("cin", C.c_int32),
+                ("cout", C.c_int32), ("cout_real", C.c_int32), ("src", C.c_int32), ("dst", C.c_int32),
+                ("res", C.c_int32), ("impl", C.c_int32), ("w_offset", C.c_int64), ("b_offset", C.c_int64),
+                ("lay_src", VolLayout), ("lay_dst", VolLayout)]
+
+
+OP_CONV, OP_MAXPOOL2, OP_DECONV2 = 0, 1, 2
+F_RELU, F_RESIDUAL, F_ADD_AFTER, F_OUT_F32 = 1, 2, 4, 8
+
+_lib = None
+
+
+class SceneEgoError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Load the shared library (no compute is performed)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise SceneEgoError(
+            f"{p} not found: build it with `python -m sceneego_b200.build` "
+            "(sceneego_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(p)
+    lib.sceneego_last_error.restype = C.c_char_p
+    lib.sceneego_vol_layout_make.restype = C.c_int64
+    lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
+    if lib.sceneego_abi_version() != 1:
+        raise SceneEgoError("libsceneego_b200.so ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().sceneego_last_error().decode()
+        if rc == -3:
+            raise Exception("norm is zero!")  # same exception text as FishEyeCalibrated.py:177
+        raise SceneEgoError(f"{what} failed (code {rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise SceneEgoError("sceneego_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise SceneEgoError("sceneego_b200 ops need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_calib(cx, cy, c2w, w2c, width, height) -> Calib:
+    c = Calib()
+    c.cx, c.cy = float(cx), float(cy)
+    for i in range(7):
+        c.c2w[i] = float(c2w[i])
+    for i in range(11):
+        c.w2c[i] = float(w2c[i])
+    c.width, c.height = int(width), int(height)
+    return c
+
+
+def vol_layout(side: int, pad: int, batch: int) -> VolLayout:
+    lay = VolLayout()
+    rc = load_library().sceneego_vol_layout_make(int(side), int(pad), int(batch), C.byref(lay))
+    if rc < 0:
+        raise SceneEgoError("vol_layout_make: bad arguments")
+    return lay
+
+
+def alloc_volume(lay: VolLayout, channels: int, device) -> torch.Tensor:
+    """Zero-initialised planar padded bf16 volume: (C/8, plane_stride, 8)."""
+    assert channels % 8 == 0
+    return torch.zeros(channels // 8, lay.plane_stride, 8, dtype=torch.bfloat16, device=device)
+
+
+# ---- thin per-op wrappers (argument checking lives in C) ---------------------
+def ray_table(calib: Calib, device) -> torch.Tensor:
+    out = torch.empty(calib.height, calib.width, 3, dtype=torch.float64, device=device)
+    _check(load_library().sceneego_ray_table_f64(C.byref(calib), _ptr(out), _stream()), "ray_table")
+    return out
+
+
+def project_voxels(calib: Calib, volume_size: int, cuboid_side: float, heatmap_shape, device):
+    n = volume_size ** 3
+    px = torch.empty(n, 2, dtype=torch.float32, device=device)
+    grid = torch.empty(n, 2, dtype=torch.float32, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    _check(load_library().sceneego_project_voxels_f32(
+        C.byref(calib), int(volume_size), C.c_float(cuboid_side), int(heatmap_shape[0]), int(heatmap_shape[1]),
+        _ptr(px), _ptr(grid), _ptr(status), _stream()), "project_voxels")
+    if int(status.item()) != 0:
+        raise Exception("norm is zero!")
+    return px, grid
+
+
+def world2camera(calib: Calib, points: torch.Tensor) -> torch.Tensor:
+    n = points.shape[0]
+    px = torch.empty(n, 2, dtype=torch.float32, device=points.device)
+    status = torch.zeros(1, dtype=torch.int32, device=points.device)
+    _check(load_library().sceneego_world2camera_f32(C.byref(calib), _ptr(points), n, _ptr(px), _ptr(status),
+                                                    _stream()), "world2camera")
+    if int(status.item()) != 0:
+        raise Exception("norm is zero!")
+    return px
+
+
+def grid_sample(img: torch.Tensor, grid: torch.Tensor, grid_batch_stride: int) -> torch.Tensor:
+    b, c, h, w = img.shape
+    n = grid.shape[-3] if grid.dim() == 4 else grid.shape[0]
+    out = torch.empty(b, c, n, dtype=torch.float32, device=img.device)
+    _check(load_library().sceneego_grid_sample_f32(_ptr(img), C.c_void_p(grid.data_ptr()),
+                                                   C.c_int64(grid_batch_stride), b, c, h, w, n, _ptr(out),
+                                                   _stream()), "grid_sample")
+    return out
+
+
+def feature_conv1x1(feat: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    b, cin, h, w = feat.shape
+    cout = weight.shape[0]
+    out = torch.empty(b, h, w, cout, dtype=torch.float32, device=feat.device)
+    _check(load_library().sceneego_feature_conv1x1_f32(
+        _ptr(feat), _ptr(weight.reshape(cout, cin)), _ptr(bias), _ptr(out), b, cin, cout, h, w, _stream()),
+        "feature_conv1x1")
+    return out
+
+
+def features_upsample_pad(feat_cl: torch.Tensor, up: int, pad: int) -> torch.Tensor:
+    b, h, w, c = feat_cl.shape
+    out = torch.empty(b, c, up, up + 2 * pad, dtype=torch.float32, device=feat_cl.device)
+    _check(load_library().sceneego_features_upsample_pad_f32(_ptr(feat_cl), _ptr(out), b, c, h, w, up, pad,
+                                                              _stream()), "features_upsample_pad")
+    return out
+
+
+def unproject(feat_cl: torch.Tensor, grid: Optional[torch.Tensor], calib: Optional[Calib], volume_size: int,
+              cuboid_side: float, img_h: int, img_w: int, out_f32: Optional[torch.Tensor],
+              out_bf16: Optional[torch.Tensor], lay: Optional[VolLayout], extra_zero_planes: int = 0) -> None:
+    b, h, w, c = feat_cl.shape
+    _check(load_library().sceneego_unproject_f32(
+        _ptr(feat_cl), _ptr(grid), C.byref(calib) if calib is not None else None, b, h, w, c, int(volume_size),
+        C.c_float(cuboid_side), int(img_h), int(img_w), _ptr(out_f32), _ptr(out_bf16),
+        C.byref(lay) if lay is not None else None, int(extra_zero_planes), _stream()), "unproject")
+
+
+def voxelize_depth(depth: torch.Tensor, ray: torch.Tensor, img_h: int, img_w: int, volume_size: int,
+                   cuboid_side: float, occ_f32: Optional[torch.Tensor], occ_bf16: Optional[torch.Tensor],
+                   lay: Optional[VolLayout], channel: int = 0) -> None:
+    b, h, w = depth.shape
+    _check(load_library().sceneego_voxelize_depth_f64(
+        _ptr(depth), b, h, w, _ptr(ray), int(img_h), int(img_w), int(volume_size), C.c_double(cuboid_side),
+        _ptr(occ_f32), _ptr(occ_bf16), C.byref(lay) if lay is not None else None, int(channel), _stream()),
+        "voxelize_depth")
+
+
+def pack_volume(x: torch.Tensor, out_bf16: torch.Tensor, lay: VolLayout, c_offset: int = 0) -> None:
+    b, c = x.shape[:2]
+    _check(load_library().sceneego_pack_volume_bf16(_ptr(x), b, c, int(c_offset), _ptr(out_bf16), C.byref(lay),
+                                                    _stream()), "pack_volume")
+
+
+def unpack_volume(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int) -> torch.Tensor:
+    s = lay.side
+    out = torch.empty(batch, channels, s, s, s, dtype=torch.float32, device=vol_bf16.device)
+    _check(load_library().sceneego_unpack_volume_f32(_ptr(vol_bf16), C.byref(lay), batch, channels, _ptr(out),
+                                                     _stream()), "unpack_volume")
+    return out
+
+
+def softargmax3d(logits: torch.Tensor, multiplier: float, softmax: bool, axis: Optional[torch.Tensor],
+                 coords: Optional[torch.Tensor], want_volumes: bool):
+    b, j, v = logits.shape[0], logits.shape[1], logits.shape[2]
+    lib = load_library()
+    ws = torch.empty(lib.sceneego_softargmax_workspace_bytes(b, j, v) // 4, dtype=torch.float32,
+                     device=logits.device)
+    kp = torch.empty(b, j, 3, dtype=torch.float32, device=logits.device)
+    vol = torch.empty_like(logits) if want_volumes else None
+    _check(lib.sceneego_softargmax3d_f32(_ptr(logits), b, j, v, C.c_float(multiplier), int(bool(softmax)),
+                                         _ptr(axis), _ptr(coords), _ptr(kp), _ptr(vol), _ptr(ws), _stream()),
+           "softargmax3d")
+    return kp, vol

@@ -88,6 +88,51 @@ __global__ void project_voxels_kernel(W2CF32 k, int V, float lo, float step, int
   }
 }
 
+// Arbitrary points (N,3) -> pixels (N,2): FishEyeCameraCalibrated.world2camera_pytorch.
+__global__ void world2camera_kernel(W2CF32 k, const float* __restrict__ pts, int n_pts, float* __restrict__ px_out,
+                                    int* __restrict__ status) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_pts) return;
+  float px, py;
+  const bool ok = project_voxel(k, pts[3 * n], pts[3 * n + 1], pts[3 * n + 2], px, py);
+  if (!ok && status) atomicExch(status, 1);
+  px_out[2 * n] = px;
+  px_out[2 * n + 1] = py;
+}
+
+// Generic F.grid_sample(bilinear, zeros, align_corners=True) on an NCHW f32 image with a grid
+// shared by the batch (utils/op.py:194-214 called on a materialised feature map).  One thread =
+// one sample point, looping over channels; consecutive points are neighbours in the image.
+__global__ void __launch_bounds__(256) grid_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid,
+                                                         int64_t grid_batch_stride, int C, int H, int W, int N,
+                                                         float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= N) return;
+  const float2 g = reinterpret_cast<const float2*>(grid + (size_t)b * grid_batch_stride)[n];
+  const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(g.x, 1.0f), 2.0f), (float)(W - 1));
+  const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(g.y, 1.0f), 2.0f), (float)(H - 1));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float wx1 = ix - x0f, wy1 = iy - y0f, wx0 = (x0f + 1.0f) - ix, wy0 = (y0f + 1.0f) - iy;
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  float wt[4];
+  int off[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int X = x0 + (t & 1), Y = y0 + (t >> 1);
+    const bool inb = X >= 0 && X < W && Y >= 0 && Y < H;
+    wt[t] = inb ? ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0) : 0.f;
+    off[t] = inb ? Y * W + X : 0;
+  }
+  const float* ib = img + (size_t)b * C * H * W;
+  for (int c = 0; c < C; ++c) {
+    const float* pl = ib + (size_t)c * H * W;
+    const float v = __ldg(pl + off[0]) * wt[0] + __ldg(pl + off[1]) * wt[1] + __ldg(pl + off[2]) * wt[2] +
+                    __ldg(pl + off[3]) * wt[3];
+    __stcs(out + ((size_t)b * C + c) * N + n, v);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // a1: 1x1 Conv2d 256 -> 32 (+bias), NCHW f32 in, channel-last f32 out.
 // One CTA = 64 pixels x 32 output channels; K streamed through smem in chunks of 32.
@@ -168,7 +213,7 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
                                                        W2CF32 cam, int h, int w, int V, float lo, float step,
                                                        int img_h, int img_w, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16,
-                                                       sceneego_vol_layout_t lay) {
+                                                       sceneego_vol_layout_t lay, int extra_zero_planes) {
   constexpr int C = 32;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
@@ -232,6 +277,9 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
       *reinterpret_cast<uint4*>(out_bf16 + ((int64_t)g * lay.plane_stride + pos) * 8) =
           *reinterpret_cast<const uint4*>(pk);
     }
+    // scene-occupancy plane(s) behind the features: cleared here, set by voxelize_kernel
+    for (int g = C / 8; g < C / 8 + extra_zero_planes; ++g)
+      *reinterpret_cast<uint4*>(out_bf16 + ((int64_t)g * lay.plane_stride + pos) * 8) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -378,7 +426,7 @@ extern "C" int sceneego_features_upsample_pad_f32(const float* d_in, float* d_ou
 extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, const sceneego_calib_t* calib,
                                       int batch, int h, int w, int c, int V, float side, int img_h, int img_w,
                                       float* d_out_f32, void* d_out_bf16, const sceneego_vol_layout_t* lay,
-                                      void* stream) {
+                                      int extra_zero_planes, void* stream) {
   SE_REQUIRE(d_feat && (d_grid || calib) && (d_out_f32 || d_out_bf16), "unproject: null argument");
   SE_REQUIRE(c == 32, "unproject: 32 feature channels expected (process_features output)");
   SE_REQUIRE(!d_out_bf16 || (lay && lay->side == V), "unproject: bf16 output needs a matching layout");
@@ -391,10 +439,12 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
   W2CF32 cam = calib ? make_w2c(calib) : W2CF32{};
   if (d_grid)
     unproject_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, d_grid, cam, h, w, V, lo, step, img_h,
-                                                                    img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L);
+                                                                    img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
+                                                                    extra_zero_planes);
   else
     unproject_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, nullptr, cam, h, w, V, lo, step, img_h,
-                                                                   img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L);
+                                                                   img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
+                                                                   extra_zero_planes);
   SE_CUDA_LAUNCH_CHECK("unproject");
   return SCENEEGO_OK;
 }
@@ -431,5 +481,24 @@ extern "C" int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_l
   unpack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_in,
                                                                                         *lay, c, d_out);
   SE_CUDA_LAUNCH_CHECK("unpack_volume");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_world2camera_f32(const sceneego_calib_t* calib, const float* d_points, int n_points,
+                                         float* d_px, int32_t* d_status, void* stream) {
+  SE_REQUIRE(calib && d_points && d_px && n_points > 0, "world2camera: bad argument");
+  world2camera_kernel<<<(n_points + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_w2c(calib), d_points, n_points,
+                                                                                d_px, d_status);
+  SE_CUDA_LAUNCH_CHECK("world2camera");
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_grid_sample_f32(const float* d_img, const float* d_grid, int64_t grid_batch_stride, int batch,
+                                        int c, int h, int w, int n_points, float* d_out, void* stream) {
+  SE_REQUIRE(d_img && d_grid && d_out, "grid_sample: null argument");
+  SE_REQUIRE(batch > 0 && batch <= 65535 && c > 0 && h > 1 && w > 1 && n_points > 0, "grid_sample: bad shape");
+  grid_sample_kernel<<<dim3((n_points + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>(
+      d_img, d_grid, grid_batch_stride, c, h, w, n_points, d_out);
+  SE_CUDA_LAUNCH_CHECK("grid_sample");
   return SCENEEGO_OK;
 }

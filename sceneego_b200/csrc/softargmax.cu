@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(SA_THREADS) softargmax_partial_kernel(
       float mx = a.m;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)) * mult);
+        if (idx[u] < end / 4)
+          mx = fmaxf(mx, fmaxf(fmaxf(v[u].x * mult, v[u].y * mult), fmaxf(v[u].z * mult, v[u].w * mult)));
       if (mx > a.m) {
         const float f = (a.m == -INFINITY) ? 0.f : exp2f((a.m - mx) * kLog2e);
         a.s *= f; a.sx *= f; a.sy *= f; a.sz *= f;

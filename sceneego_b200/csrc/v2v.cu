@@ -1,0 +1,639 @@
+// a7: V2V encoder-decoder (network/v2v.py) on sm_100a.
+//
+// Data layout ("planar padded"): a volume with C channels is stored as C/8
+// planes; a plane is a linear array of 16-byte cells (8 bf16 channels of one voxel)
+// indexed by a POSITION  q = b*frame_pitch + guard + x*pitch_x + y*pitch_y + z,
+// where every z-line is followed by `pad` zero cells and every x-plane by `pad` zero
+// lines, and every frame is preceded by `guard` zero cells.  With the zeros physically
+// present, a conv tap (dx,dy,dz) is the constant position offset dx*pitch_x+dy*pitch_y+dz:
+// "same" padding needs no masks, and the A operand of the implicit GEMM for any tap is
+// just the staged window shifted by a multiple of 16 bytes.
+//
+// conv_tc_kernel: persistent, warp-specialised implicit GEMM.
+//   rows (M)   = 128 consecutive positions per UMMA tile, `tiles` tiles per work item
+//   cols (N)   = Cout (16..128)
+//   reduction  = taps x Cin, 16 channels (two 8-channel planes) per tcgen05.mma
+//   warp 0     = producer: cp.async.bulk (TMA 1-D) of the per-dx activation window
+//                (one contiguous run per channel plane) and of the weight chunks
+//   warp 1     = TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2-5  = epilogue: tcgen05.ld -> bias / residual / ReLU / pad-zeroing -> bf16 planes
+//   smem operands use the no-swizzle K-major canonical layout: 8 rows x 16 B core matrices,
+//   SBO = 128 B between 8-row groups, LBO = plane stride between the two K chunks.
+//   Accumulators: 2 x (tiles x N) fp32 columns of TMEM, double-buffered across work items.
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+namespace sceneego {
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      printf("sceneego conv_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 format, version 1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// ---------------------------------------------------------------------------
+// conv parameters
+// ---------------------------------------------------------------------------
+struct ConvParams {
+  const __nv_bfloat16* src;
+  __nv_bfloat16* dst;
+  const __nv_bfloat16* res;
+  float* dst_f32;
+  const __nv_bfloat16* w;   // [tap][cin/8][cout][8]
+  const float* bias;        // [cout]
+  sceneego_vol_layout_t ls, ld;
+  int batch;
+  int k, r, cin_planes, ksteps, N, cout_real, flags;
+  int tiles, L, WL;                 // tiles per item, positions per item, window length (positions)
+  int n_items;
+  int win_stages, w_slots, wchunk_taps, wchunks_per_dx;
+  uint32_t win_bytes, wchunk_bytes, tap_bytes;
+  uint32_t off_win, off_w, off_bias, off_bar;
+  uint32_t tmem_cols, half_cols;
+  int swap_lbo_sbo;                 // debug switch for descriptor-field validation
+};
+
+constexpr int CONV_THREADS = 192;
+constexpr int MAX_STAGES = 4, MAX_WSLOTS = 8;
+
+struct RowInfo {
+  bool write;    // position belongs to a frame (valid voxel or in-frame pad)
+  bool valid;    // a real voxel
+  int b, n;      // frame and flat voxel index (valid only)
+  int64_t dpos;  // position in the destination layout
+};
+
+__device__ __forceinline__ RowInfo decode_row(const ConvParams& p, int64_t q) {
+  RowInfo ri;
+  ri.write = false; ri.valid = false; ri.b = 0; ri.n = 0; ri.dpos = 0;
+  const int S = p.ls.side;
+  const int64_t b = q / p.ls.frame_pitch;
+  const int rem = (int)(q - b * p.ls.frame_pitch) - p.ls.guard;
+  if (b >= p.batch || rem < 0) return ri;
+  const int x = rem / p.ls.pitch_x;
+  const int r2 = rem - x * p.ls.pitch_x;
+  const int y = r2 / p.ls.pitch_y;
+  const int z = r2 - y * p.ls.pitch_y;
+  if (x >= S) return ri;
+  // cells of the destination layout reachable from this source cell: voxels and the
+  // destination's own pad cells (kept zero so the next conv can use them as padding)
+  if (y >= S + p.ld.pad || z >= S + p.ld.pad) return ri;
+  ri.write = true;
+  ri.valid = (y < S) && (z < S);
+  ri.b = (int)b;
+  ri.n = (x * S + y) * S + z;
+  ri.dpos = b * p.ld.frame_pitch + p.ld.guard + (int64_t)x * p.ld.pitch_x + (int64_t)y * p.ld.pitch_y + z;
+  return ri;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  __align__(16) __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return *reinterpret_cast<const uint4*>(h);
+}
+
+// Shared epilogue: v[0..15] are output channels c0..c0+15 of one row.
+__device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& ri, int c0, float (&v)[16],
+                                            const float* s_bias) {
+  if (!ri.write) return;
+  const int S = p.ls.side;
+  if (p.flags & SCENEEGO_F_OUT_F32) {
+    if (!ri.valid) return;
+    const size_t N3 = (size_t)S * S * S;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = c0 + j;
+      if (c < p.cout_real) {
+        float o = v[j] + s_bias[c];
+        if (p.flags & SCENEEGO_F_RELU) o = fmaxf(o, 0.f);
+        p.dst_f32[((size_t)ri.b * p.cout_real + c) * N3 + ri.n] = o;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float o[8];
+    const int64_t cell = (int64_t)((c0 >> 3) + g) * p.ld.plane_stride + ri.dpos;
+    if (ri.valid) {
+      float rr[8];
+      const bool has_res = (p.flags & (SCENEEGO_F_RESIDUAL | SCENEEGO_F_ADD_AFTER)) != 0;
+      if (has_res) unpack8(*reinterpret_cast<const uint4*>(p.res + cell * 8), rr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = v[8 * g + j] + s_bias[c0 + 8 * g + j];
+        if (p.flags & SCENEEGO_F_RESIDUAL) t += rr[j];
+        if (p.flags & SCENEEGO_F_RELU) t = fmaxf(t, 0.f);
+        if (p.flags & SCENEEGO_F_ADD_AFTER) t += rr[j];
+        o[j] = t;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(p.dst + cell * 8) = pack8(o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 implicit-GEMM conv
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  // barrier map
+  const uint32_t bar0 = sbase + p.off_bar;
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int B_FULL_WIN = 0, B_EMPTY_WIN = MAX_STAGES, B_FULL_W = 2 * MAX_STAGES, B_EMPTY_W = 2 * MAX_STAGES + MAX_WSLOTS,
+            B_TMEM_FULL = 2 * MAX_STAGES + 2 * MAX_WSLOTS, B_TMEM_EMPTY = B_TMEM_FULL + 2, B_COUNT = B_TMEM_EMPTY + 2;
+  uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  for (int i = threadIdx.x; i < p.N; i += CONV_THREADS) s_bias[i] = p.bias[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), 1); mbar_init(BAR(B_EMPTY_WIN + i), 1); }
+    for (int i = 0; i < MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), 1); mbar_init(BAR(B_EMPTY_W + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), 1); mbar_init(BAR(B_TMEM_EMPTY + i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem_ptr;
+
+  const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int halo = p.r * (p.ls.pitch_y + 1);   // window starts `halo` positions before the item
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int ws = 0, wph = 0, sl = 0, sph = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * p.L;
+        for (int dx = 0; dx < p.k; ++dx) {
+          mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
+          mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * p.cin_planes);
+          const int64_t qs = q0 + (int64_t)(dx - p.r) * p.ls.pitch_x - halo;
+          for (int g = 0; g < p.cin_planes; ++g)
+            bulk_g2s(sbase + p.off_win + (uint32_t)(ws * p.cin_planes + g) * p.win_bytes,
+                     p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8, p.win_bytes, BAR(B_FULL_WIN + ws));
+          if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+          for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
+            mbar_wait(BAR(B_EMPTY_W + sl), sph ^ 1);
+            mbar_expect_tx(BAR(B_FULL_W + sl), p.wchunk_bytes);
+            const char* wsrc = reinterpret_cast<const char*>(p.w) +
+                               (size_t)(dx * p.wchunks_per_dx + wc) * p.wchunk_bytes;
+            bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes, wsrc, p.wchunk_bytes, BAR(B_FULL_W + sl));
+            if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=p.N
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
+      const uint32_t a_lbo = p.swap_lbo_sbo ? 128u : p.win_bytes;
+      const uint32_t a_sbo = p.swap_lbo_sbo ? p.win_bytes : 128u;
+      const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.N * 16u;
+      const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)p.N * 16u : 128u;
+      int ws = 0, wph = 0, sl = 0, sph = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int buf = it & 1;
+        mbar_wait(BAR(B_TMEM_EMPTY + buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)buf * p.half_cols;
+        uint32_t acc = 0;
+        for (int dx = 0; dx < p.k; ++dx) {
+          mbar_wait(BAR(B_FULL_WIN + ws), wph);
+          const uint32_t win = sbase + p.off_win + (uint32_t)(ws * p.cin_planes) * p.win_bytes;
+          for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
+            mbar_wait(BAR(B_FULL_W + sl), sph);
+            tc_fence_after();
+            const uint32_t wsm = sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes;
+            for (int tt = 0; tt < p.wchunk_taps; ++tt) {
+              const int tap = wc * p.wchunk_taps + tt;     // index inside this dx: dy*k + dz
+              const int dy = tap / p.k, dz = tap - dy * p.k;
+              const uint32_t rowoff = (uint32_t)(dy * p.ls.pitch_y + dz) * 16u;
+              for (int t = 0; t < p.tiles; ++t) {
+                for (int ks = 0; ks < p.ksteps; ++ks) {
+                  const uint64_t ad = make_desc(win + rowoff + (uint32_t)t * 2048u + (uint32_t)(2 * ks) * p.win_bytes,
+                                                a_lbo, a_sbo);
+                  const uint64_t bd = make_desc(wsm + (uint32_t)tt * p.tap_bytes + (uint32_t)(2 * ks) * (uint32_t)p.N * 16u,
+                                                b_lbo, b_sbo);
+                  tc_mma_bf16(d0 + (uint32_t)(t * p.N), ad, bd, idesc, acc | (uint32_t)ks);
+                }
+              }
+              acc = 1;
+            }
+            tc_commit(BAR(B_EMPTY_W + sl));
+            if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+          }
+          tc_commit(BAR(B_EMPTY_WIN + ws));
+          if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+        }
+        tc_commit(BAR(B_TMEM_FULL + buf));
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    for (int it = 0; it < my_items; ++it) {
+      const int buf = it & 1;
+      const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * p.L;
+      mbar_wait(BAR(B_TMEM_FULL + buf), (it >> 1) & 1);
+      tc_fence_after();
+      for (int t = 0; t < p.tiles; ++t) {
+        const RowInfo ri = decode_row(p, q0 + t * 128 + quarter * 32 + lane);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * p.half_cols +
+                               (uint32_t)(t * p.N);
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t raw[16];
+          tc_ld16(taddr + (uint32_t)c0, raw);
+          tc_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          store_row16(p, ri, c0, v, s_bias);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_TMEM_EMPTY + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CUDA-core checker conv: same layouts, same packed weights, same epilogue.  Used for the
+// tiny deep levels' validation and to bisect tensor-core descriptor errors (op.impl = 1).
+// One thread = one position x 16 output channels.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ ConvParams p, int64_t n_pos) {
+  __shared__ float s_bias[128];
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias[i];
+  __syncthreads();
+  const int64_t q = (int64_t)p.ls.guard + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = blockIdx.y * 16;
+  if (q - p.ls.guard >= n_pos) return;
+  const RowInfo ri = decode_row(p, q);
+  if (!ri.write) return;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  if (ri.valid) {
+    for (int dx = 0; dx < p.k; ++dx)
+      for (int dy = 0; dy < p.k; ++dy)
+        for (int dz = 0; dz < p.k; ++dz) {
+          const int tap = (dx * p.k + dy) * p.k + dz;
+          const int64_t qs = q + (int64_t)(dx - p.r) * p.ls.pitch_x + (int64_t)(dy - p.r) * p.ls.pitch_y + (dz - p.r);
+          for (int g = 0; g < p.cin_planes; ++g) {
+            float a[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8), a);
+            const uint4* wrow = reinterpret_cast<const uint4*>(p.w) + ((size_t)tap * p.cin_planes + g) * p.N + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float wv[8];
+              unpack8(__ldg(wrow + j), wv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], wv[i], acc[j]);
+            }
+          }
+        }
+  }
+  store_row16(p, ri, c0, acc, s_bias);
+}
+
+// ---------------------------------------------------------------------------
+// 2x2x2 max-pool (network/v2v.py:46-52).  One thread = one output cell (8 channels).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16* __restrict__ src,
+                                                      __nv_bfloat16* __restrict__ dst, sceneego_vol_layout_t ls,
+                                                      sceneego_vol_layout_t ld, int planes) {
+  const int So = ld.side;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y, b = blockIdx.z;
+  if (n >= So * So * So || g >= planes) return;
+  const int z = n % So, y = (n / So) % So, x = n / (So * So);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int64_t q = vol_pos(ls, b, 2 * x + (t >> 2), 2 * y + ((t >> 1) & 1), 2 * z + (t & 1));
+    float a[8];
+    unpack8(*reinterpret_cast<const uint4*>(src + ((int64_t)g * ls.plane_stride + q) * 8), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], a[j]);
+  }
+  *reinterpret_cast<uint4*>(dst + ((int64_t)g * ld.plane_stride + vol_pos(ld, b, x, y, z)) * 8) = pack8(m);
+}
+
+// ---------------------------------------------------------------------------
+// ConvTranspose3d k2 s2 + folded BN + ReLU, then + skip (network/v2v.py:55-67,125-137).
+// out[co, 2x+i, 2y+j, 2z+l] = relu(sum_ci W[parity][ci][co] * in[ci,x,y,z] + b[co]) + skip.
+// One thread = one output cell x 8 output channels; weights packed like a conv with 8 taps.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) deconv2_kernel(const __grid_constant__ ConvParams p) {
+  const int So = p.ld.side;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int go = blockIdx.y, b = blockIdx.z;
+  if (n >= So * So * So) return;
+  const int z = n % So, y = (n / So) % So, x = n / (So * So);
+  const int tap = ((x & 1) * 2 + (y & 1)) * 2 + (z & 1);
+  const int64_t qs = vol_pos(p.ls, b, x >> 1, y >> 1, z >> 1);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int g = 0; g < p.cin_planes; ++g) {
+    float a[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8), a);
+    const uint4* wrow = reinterpret_cast<const uint4*>(p.w) + ((size_t)tap * p.cin_planes + g) * p.N + go * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float wv[8];
+      unpack8(__ldg(wrow + j), wv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], wv[i], acc[j]);
+    }
+  }
+  const int64_t cell = (int64_t)go * p.ld.plane_stride + vol_pos(p.ld, b, x, y, z);
+  float rr[8];
+  if (p.flags & SCENEEGO_F_ADD_AFTER) unpack8(*reinterpret_cast<const uint4*>(p.res + cell * 8), rr);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = acc[j] + p.bias[go * 8 + j];
+    if (p.flags & SCENEEGO_F_RELU) t = fmaxf(t, 0.f);
+    if (p.flags & SCENEEGO_F_ADD_AFTER) t += rr[j];
+    acc[j] = t;
+  }
+  *reinterpret_cast<uint4*>(p.dst + cell * 8) = pack8(acc);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static thread_local int g_launches = 0;
+
+static uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+constexpr uint32_t kMaxSmem = 232448;  // 227 KB
+
+// Choose tiles / stages / weight chunking for a conv and fill the kernel parameters.
+static int plan_conv(ConvParams& p) {
+  const int taps_dx = p.k * p.k;
+  p.tap_bytes = (uint32_t)p.cin_planes * p.N * 16u;
+  int max_tiles = 256 / p.N;
+  if (max_tiles > 8) max_tiles = 8;
+  for (int tiles = max_tiles; tiles >= 1; tiles >>= 1) {
+    const int L = tiles * 128;
+    const int WL = L + 2 * p.r * (p.ls.pitch_y + 1);
+    const uint32_t win_bytes = (uint32_t)WL * 16u;
+    const uint32_t stage = win_bytes * p.cin_planes;
+    // weight chunk: as many taps of one dx as fit ~24 KB, must divide k*k
+    int wct = taps_dx;
+    while (wct > 1 && (uint32_t)wct * p.tap_bytes > 24576u) {
+      int nx = wct - 1;
+      while (nx > 1 && taps_dx % nx) --nx;
+      wct = nx;
+    }
+    const uint32_t wchunk = (uint32_t)wct * p.tap_bytes;
+    for (int stages = (p.k == 1 ? 3 : 2); stages >= 2; --stages) {
+      const uint32_t fixed = 1024;  // bias + barriers + tmem ptr
+      const uint32_t used = stage * stages + fixed;
+      if (used + 2 * wchunk > kMaxSmem) continue;
+      int slots = (int)((kMaxSmem - used) / wchunk);
+      if (slots > MAX_WSLOTS) slots = MAX_WSLOTS;
+      if (slots > 4 && wchunk > 8192) slots = 4;
+      p.tiles = tiles; p.L = L; p.WL = WL;
+      p.win_bytes = win_bytes; p.win_stages = stages;
+      p.wchunk_taps = wct; p.wchunks_per_dx = taps_dx / wct; p.wchunk_bytes = wchunk; p.w_slots = slots;
+      p.off_win = 0;
+      p.off_w = stage * stages;
+      p.off_bias = p.off_w + wchunk * slots;
+      p.off_bar = p.off_bias + 512;
+      p.half_cols = (uint32_t)(tiles * p.N);
+      uint32_t cols = 32;
+      while (cols < 2 * p.half_cols) cols <<= 1;
+      p.tmem_cols = cols;
+      return (int)(p.off_bar + 512);
+    }
+  }
+  return -1;
+}
+
+}  // namespace sceneego
+
+using namespace sceneego;
+
+extern "C" int sceneego_abi_version(void) { return SCENEEGO_ABI_VERSION; }
+extern "C" const char* sceneego_last_error(void) { return g_err; }
+extern "C" int sceneego_v2v_last_launch_count(void) { return g_launches; }
+
+extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const float* h_gamma,
+                                      const float* h_beta, const float* h_mean, const float* h_var, double eps,
+                                      int cout, int cin, int ksize, int transposed, int cout_pad, int cin_pad,
+                                      uint16_t* h_w_out, float* h_b_out) {
+  SE_REQUIRE(h_weight && h_w_out && h_b_out, "pack_conv: null argument");
+  SE_REQUIRE(cout_pad >= cout && cin_pad >= cin && cout_pad % 8 == 0 && cin_pad % 8 == 0, "pack_conv: bad padding");
+  const int taps = ksize * ksize * ksize;
+  memset(h_w_out, 0, (size_t)taps * cin_pad * cout_pad * sizeof(uint16_t));
+  for (int co = 0; co < cout_pad; ++co) {
+    double scale = 1.0, shift = 0.0;
+    if (co < cout) {
+      if (h_gamma) {
+        scale = (double)h_gamma[co] / sqrt((double)h_var[co] + eps);
+        shift = (double)h_beta[co] - (double)h_mean[co] * scale;
+      }
+      h_b_out[co] = (float)((h_bias ? (double)h_bias[co] : 0.0) * scale + shift);
+    } else {
+      h_b_out[co] = 0.f;
+    }
+    if (co >= cout) continue;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        // Conv3d (cout,cin,kx,ky,kz); ConvTranspose3d (cin,cout,kx,ky,kz): tap = output parity
+        const size_t src = transposed ? (((size_t)ci * cout + co) * taps + t) : (((size_t)co * cin + ci) * taps + t);
+        const float wv = (float)((double)h_weight[src] * scale);
+        const size_t dst = (((size_t)t * (cin_pad / 8) + ci / 8) * cout_pad + co) * 8 + (ci & 7);
+        h_w_out[dst] = f2bf(wv);
+      }
+  }
+  return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,
+                                int batch, void* stream) {
+  SE_REQUIRE(ops && d_buffers && d_blob && n_ops > 0 && batch > 0, "v2v_run: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+    attr_set = true;
+  }
+  const char* swap_env = getenv("SCENEEGO_SWAP_LBO_SBO");
+  const char* force_simt = getenv("SCENEEGO_FORCE_SIMT");
+  g_launches = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const sceneego_v2v_op_t& op = ops[i];
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = (const __nv_bfloat16*)d_buffers[op.src];
+    p.dst = (__nv_bfloat16*)d_buffers[op.dst];
+    p.dst_f32 = (float*)d_buffers[op.dst];
+    p.res = op.res >= 0 ? (const __nv_bfloat16*)d_buffers[op.res] : nullptr;
+    p.ls = op.lay_src; p.ld = op.lay_dst; p.batch = batch; p.flags = op.flags;
+    SE_REQUIRE(p.src && p.dst, "v2v_run: op %d has a null buffer", i);
+    SE_REQUIRE(!(op.flags & (SCENEEGO_F_RESIDUAL | SCENEEGO_F_ADD_AFTER)) || p.res, "v2v_run: op %d needs a residual", i);
+    if (op.type == SCENEEGO_OP_MAXPOOL2) {
+      SE_REQUIRE(op.lay_dst.side * 2 == op.lay_src.side && op.cin % 8 == 0, "v2v_run: op %d bad pool shape", i);
+      const int So = op.lay_dst.side;
+      dim3 grid((So * So * So + 255) / 256, op.cin / 8, batch);
+      maxpool2_kernel<<<grid, 256, 0, st>>>(p.src, p.dst, p.ls, p.ld, op.cin / 8);
+      SE_CUDA_LAUNCH_CHECK("maxpool2");
+      ++g_launches;
+      continue;
+    }
+    p.w = (const __nv_bfloat16*)((const char*)d_blob + op.w_offset);
+    p.bias = (const float*)((const char*)d_blob + op.b_offset);
+    p.cin_planes = op.cin / 8; p.ksteps = op.cin / 16; p.N = op.cout; p.cout_real = op.cout_real;
+    if (op.type == SCENEEGO_OP_DECONV2) {
+      SE_REQUIRE(op.lay_dst.side == 2 * op.lay_src.side && op.cin % 8 == 0 && op.cout % 8 == 0, "v2v_run: op %d bad deconv shape", i);
+      const int So = op.lay_dst.side;
+      dim3 grid((So * So * So + 127) / 128, op.cout / 8, batch);
+      deconv2_kernel<<<grid, 128, 0, st>>>(p);
+      SE_CUDA_LAUNCH_CHECK("deconv2");
+      ++g_launches;
+      continue;
+    }
+    SE_REQUIRE(op.type == SCENEEGO_OP_CONV, "v2v_run: op %d unknown type", i);
+    SE_REQUIRE(op.ksize == 1 || op.ksize == 3 || op.ksize == 7, "v2v_run: op %d unsupported kernel size", i);
+    SE_REQUIRE(op.cin % 16 == 0 && op.cout % 16 == 0 && op.cout >= 16 && op.cout <= 128, "v2v_run: op %d channels must be multiples of 16", i);
+    SE_REQUIRE(op.lay_src.side == op.lay_dst.side && op.lay_src.pad >= op.ksize / 2 && op.lay_dst.pad <= op.lay_src.pad,
+               "v2v_run: op %d layouts incompatible with the stencil", i);
+    p.k = op.ksize; p.r = op.ksize / 2;
+    const int64_t n_pos = (int64_t)batch * p.ls.frame_pitch;
+    if (op.impl == 1 || force_simt) {
+      dim3 grid((unsigned)((n_pos + 127) / 128), op.cout / 16);
+      conv_simt_kernel<<<grid, 128, 0, st>>>(p, n_pos);
+      SE_CUDA_LAUNCH_CHECK("conv_simt");
+      ++g_launches;
+      continue;
+    }
+    const int smem = plan_conv(p);
+    SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", i);
+    p.n_items = (int)((n_pos + p.L - 1) / p.L);
+    p.swap_lbo_sbo = swap_env ? atoi(swap_env) : 0;
+    const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+    conv_tc_kernel<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
+    SE_CUDA_LAUNCH_CHECK("conv_tc");
+    ++g_launches;
+  }
+  return SCENEEGO_OK;
+}

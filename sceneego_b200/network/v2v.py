@@ -1,0 +1,375 @@
+"""V2V encoder-decoder (reference: network/v2v.py:8-181) for the B200 engine.
+
+The nn.Modules below exist to own parameters and BatchNorm buffers under exactly
+the reference's state-dict names ("front_layers.0.block.0.weight", ...), so
+checkpoints load strictly.  Their forward is NOT torch: `V2VModel` compiles its
+own structure into a flat op program (conv / max-pool / deconv steps over planar
+padded bf16 buffers) that `sceneego_v2v_run` executes with hand-written sm_100a
+kernels.  BatchNorm (eval) is folded into the packed bf16 weights when the
+program is built; folded weights are derived data and never enter the state dict.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+def _conv_bn(cin, cout, k, relu):
+    layers = [nn.Conv3d(cin, cout, kernel_size=k, stride=1, padding=(k - 1) // 2), nn.BatchNorm3d(cout)]
+    if relu:
+        layers.append(nn.ReLU(True))
+    return layers
+
+
+class Basic3DBlock(nn.Module):
+    """conv(k, same) - BN - ReLU (v2v.py:8-18); children: block.0, block.1."""
+
+    def __init__(self, in_planes, out_planes, kernel_size):
+        super().__init__()
+        self.block = nn.Sequential(*_conv_bn(in_planes, out_planes, kernel_size, True))
+
+
+class Res3DBlock(nn.Module):
+    """v2v.py:21-43; children: res_branch.{0,1,3,4}, skip_con.{0,1} when channels change."""
+
+    def __init__(self, in_planes, out_planes):
+        super().__init__()
+        self.res_branch = nn.Sequential(*(_conv_bn(in_planes, out_planes, 3, True)
+                                          + _conv_bn(out_planes, out_planes, 3, False)))
+        self.skip_con = nn.Sequential() if in_planes == out_planes else nn.Sequential(
+            *_conv_bn(in_planes, out_planes, 1, False))
+
+
+class Pool3DBlock(nn.Module):
+    def __init__(self, pool_size):
+        super().__init__()
+        assert pool_size == 2
+        self.pool_size = pool_size
+
+
+class Upsample3DBlock(nn.Module):
+    """ConvTranspose3d(k2,s2) - BN - ReLU (v2v.py:55-67)."""
+
+    def __init__(self, in_planes, out_planes, kernel_size, stride):
+        super().__init__()
+        assert kernel_size == 2 and stride == 2
+        self.block = nn.Sequential(
+            nn.ConvTranspose3d(in_planes, out_planes, kernel_size=2, stride=2, padding=0, output_padding=0),
+            nn.BatchNorm3d(out_planes), nn.ReLU(True))
+
+
+class EncoderDecorder(nn.Module):  # (sic) -- the reference's spelling is part of no key, kept for familiarity
+    """v2v.py:70-139: five pool/res levels, mid res, five res/upsample levels with skips."""
+
+    CHANNELS = [32, 64, 128, 128, 128, 128]   # channels at level 0..5
+
+    def __init__(self):
+        super().__init__()
+        ch = self.CHANNELS
+        for lvl in range(1, 6):
+            setattr(self, f"encoder_pool{lvl}", Pool3DBlock(2))
+            setattr(self, f"encoder_res{lvl}", Res3DBlock(ch[lvl - 1], ch[lvl]))
+        self.mid_res = Res3DBlock(128, 128)
+        for lvl in range(5, 0, -1):
+            setattr(self, f"decoder_res{lvl}", Res3DBlock(ch[lvl], ch[lvl]))
+            setattr(self, f"decoder_upsample{lvl}", Upsample3DBlock(ch[lvl], ch[lvl - 1], 2, 2))
+        for lvl in range(1, 6):
+            setattr(self, f"skip_res{lvl}", Res3DBlock(ch[lvl - 1], ch[lvl - 1]))
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class _Program:
+    """Op list + buffer pool + packed weight blob for one (volume_size, chunk) pair."""
+
+    def __init__(self, side: int, chunk: int, in_channels: int, device):
+        self.side, self.chunk, self.device = side, chunk, device
+        self.ops: List[_lib.V2VOp] = []
+        self.buffers: List[torch.Tensor] = []
+        self.buf_level: List[int] = []
+        self.free: Dict[int, List[int]] = {}
+        self.blob_parts: List[np.ndarray] = []
+        self.blob_bytes = 0
+        self.in_channels = in_channels
+        self.in_pad = _pad16(in_channels)
+        self.lay_in = _lib.vol_layout(side, 3, chunk)          # stem input: 7^3 stencil needs 3 zero cells
+        self.lays = [_lib.vol_layout(side >> l, 1, chunk) for l in range(6)]
+        self.level_channels = EncoderDecorder.CHANNELS
+        self.in_buf = self._new_buffer(-1)
+        self.logits_buf: Optional[int] = None
+        self.flops = 0
+
+    # -- buffers -------------------------------------------------------------
+    def _new_buffer(self, level: int) -> int:
+        if level < 0:
+            t = _lib.alloc_volume(self.lay_in, self.in_pad, self.device)
+        else:
+            t = _lib.alloc_volume(self.lays[level], self.level_channels[level], self.device)
+        self.buffers.append(t)
+        self.buf_level.append(level)
+        return len(self.buffers) - 1
+
+    def acquire(self, level: int) -> int:
+        pool = self.free.setdefault(level, [])
+        return pool.pop() if pool else self._new_buffer(level)
+
+    def release(self, idx: int) -> None:
+        self.free.setdefault(self.buf_level[idx], []).append(idx)
+
+    def lay_of(self, idx: int):
+        lvl = self.buf_level[idx]
+        return self.lay_in if lvl < 0 else self.lays[lvl]
+
+    # -- weights -------------------------------------------------------------
+    def _append_blob(self, arr: np.ndarray) -> int:
+        off = self.blob_bytes
+        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        padn = (-raw.size) % 256
+        if padn:
+            raw = np.concatenate([raw, np.zeros(padn, np.uint8)])
+        self.blob_parts.append(raw)
+        self.blob_bytes += raw.size
+        return off
+
+    def pack(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int) -> Tuple[int, int]:
+        transposed = isinstance(conv, nn.ConvTranspose3d)
+        w = conv.weight.detach().float().cpu().contiguous().numpy()
+        k = w.shape[-1]
+        cin, cout = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
+        bias = conv.bias.detach().float().cpu().contiguous().numpy() if conv.bias is not None else None
+        taps = k ** 3
+        w_out = np.zeros(taps * cin_pad * cout_pad, dtype=np.uint16)
+        b_out = np.zeros(cout_pad, dtype=np.float32)
+
+        def fp(a):
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        if bn is not None:
+            g = bn.weight.detach().float().cpu().contiguous().numpy()
+            bt = bn.bias.detach().float().cpu().contiguous().numpy()
+            mu = bn.running_mean.detach().float().cpu().contiguous().numpy()
+            var = bn.running_var.detach().float().cpu().contiguous().numpy()
+            eps = float(bn.eps)
+        else:
+            g = bt = mu = var = None
+            eps = 0.0
+        rc = _lib.load_library().sceneego_v2v_pack_conv(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var),
+                                                        C.c_double(eps), cout, cin, k, int(transposed), cout_pad,
+                                                        cin_pad, fp(w_out), fp(b_out))
+        _lib._check(rc, "v2v_pack_conv")
+        return self._append_blob(w_out), self._append_blob(b_out)
+
+    # -- ops -----------------------------------------------------------------
+    def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False):
+        k = conv.kernel_size[0]
+        cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
+        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad)
+        op = _lib.V2VOp()
+        op.type = _lib.OP_CONV
+        op.flags = (_lib.F_RELU if relu else 0) | (_lib.F_RESIDUAL if res >= 0 else 0) | (_lib.F_OUT_F32 if out_f32 else 0)
+        op.ksize, op.cin, op.cout, op.cout_real = k, cin_pad, cout_pad, conv.out_channels
+        op.src, op.dst, op.res, op.impl = src, dst, res, 0
+        op.w_offset, op.b_offset = w_off, b_off
+        op.lay_src = self.lay_of(src)
+        op.lay_dst = self.lay_of(dst) if not out_f32 else self.lay_of(src)
+        self.ops.append(op)
+        self.flops += 2 * conv.in_channels * conv.out_channels * k ** 3 * op.lay_src.side ** 3
+
+    def pool(self, src: int, dst: int, channels: int):
+        op = _lib.V2VOp()
+        op.type, op.cin, op.cout, op.cout_real = _lib.OP_MAXPOOL2, channels, channels, channels
+        op.src, op.dst, op.res = src, dst, -1
+        op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
+        self.ops.append(op)
+
+    def deconv(self, conv: nn.ConvTranspose3d, bn, src: int, dst: int, add: int):
+        cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
+        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad)
+        op = _lib.V2VOp()
+        op.type = _lib.OP_DECONV2
+        op.flags = _lib.F_RELU | (_lib.F_ADD_AFTER if add >= 0 else 0)
+        op.ksize, op.cin, op.cout, op.cout_real = 2, cin_pad, cout_pad, conv.out_channels
+        op.src, op.dst, op.res = src, dst, add
+        op.w_offset, op.b_offset = w_off, b_off
+        op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
+        self.ops.append(op)
+        self.flops += 2 * conv.in_channels * conv.out_channels * 8 * op.lay_src.side ** 3
+
+    def finalize(self):
+        self.blob = torch.from_numpy(np.concatenate(self.blob_parts)).to(self.device)
+        self.op_array = (_lib.V2VOp * len(self.ops))(*self.ops)
+        self.buf_ptrs = (C.c_void_p * len(self.buffers))(*[C.c_void_p(t.data_ptr()) for t in self.buffers])
+        self.blob_parts = []
+
+
+class V2VModel(nn.Module):
+    """network/v2v.py:142-181.  forward(x) takes (B,C,V,V,V) f32 like the reference and
+    returns (B,out,V,V,V) f32 logits; the fused path used by VoxelNetwork_depth writes the
+    stem input directly (see `input_buffer`) and calls `run_chunk`."""
+
+    def __init__(self, input_channels, output_channels, max_chunk: int = 16):
+        super().__init__()
+        self.input_channels, self.output_channels = input_channels, output_channels
+        self.max_chunk = max_chunk
+        self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
+                                          Res3DBlock(32, 32), Res3DBlock(32, 32))
+        self.encoder_decoder = EncoderDecorder()
+        self.back_layers = nn.Sequential(Res3DBlock(32, 32), Basic3DBlock(32, 32, 1), Basic3DBlock(32, 32, 1))
+        self.output_layer = nn.Conv3d(32, output_channels, kernel_size=1, stride=1, padding=0)
+        self._initialize_weights()
+        self._programs: Dict[Tuple[int, int], _Program] = {}
+        self._weights_version = None
+
+    def _initialize_weights(self):
+        # v2v.py:172-181
+        for m in self.modules():
+            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+                nn.init.xavier_normal_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    # -- program construction --------------------------------------------------
+    def invalidate(self):
+        """Drop packed weights (call after changing parameters in place)."""
+        self._programs.clear()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._programs.clear()
+
+    def _res(self, pg: _Program, blk: Res3DBlock, x: int, level: int) -> int:
+        t = pg.acquire(level)
+        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True)
+        if len(blk.skip_con) > 0:
+            s = pg.acquire(level)
+            pg.conv(blk.skip_con[0], blk.skip_con[1], x, s, relu=False)
+        else:
+            s = x
+        y = pg.acquire(level)
+        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s)
+        pg.release(t)
+        if s != x:
+            pg.release(s)
+        return y
+
+    def _build(self, side: int, chunk: int, device) -> _Program:
+        if side % 32 != 0:
+            raise _lib.SceneEgoError("V2V needs a volume side divisible by 32 (five 2x poolings)")
+        pg = _Program(side, chunk, self.input_channels, device)
+        ed = self.encoder_decoder
+        x = pg.acquire(0)
+        pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True)
+        for i in (1, 2, 3):
+            y = self._res(pg, self.front_layers[i], x, 0)
+            pg.release(x)
+            x = y
+        skips = []
+        for lvl in range(1, 6):
+            skips.append(self._res(pg, getattr(ed, f"skip_res{lvl}"), x, lvl - 1))
+            p = pg.acquire(lvl)
+            pg.pool(x, p, EncoderDecorder.CHANNELS[lvl - 1])
+            pg.release(x)
+            x = self._res(pg, getattr(ed, f"encoder_res{lvl}"), p, lvl)
+            pg.release(p)
+        y = self._res(pg, ed.mid_res, x, 5)
+        pg.release(x)
+        x = y
+        for lvl in range(5, 0, -1):
+            y = self._res(pg, getattr(ed, f"decoder_res{lvl}"), x, lvl)
+            pg.release(x)
+            up = getattr(ed, f"decoder_upsample{lvl}")
+            u = pg.acquire(lvl - 1)
+            pg.deconv(up.block[0], up.block[1], y, u, add=skips[lvl - 1])
+            pg.release(y)
+            pg.release(skips[lvl - 1])
+            x = u
+        y = self._res(pg, self.back_layers[0], x, 0)
+        pg.release(x)
+        x = y
+        for i in (1, 2):
+            y = pg.acquire(0)
+            pg.conv(self.back_layers[i].block[0], self.back_layers[i].block[1], x, y, relu=True)
+            pg.release(x)
+            x = y
+        # output layer writes f32 logits (B,J,V,V,V); its dst buffer slot is patched per call
+        pg.buffers.append(torch.empty(0, device=device))
+        pg.buf_level.append(0)
+        pg.logits_buf = len(pg.buffers) - 1
+        pg.conv(self.output_layer, None, x, pg.logits_buf, relu=False, out_f32=True)
+        pg.finalize()
+        return pg
+
+    def program(self, side: int, chunk: int, device) -> _Program:
+        key = (side, chunk)
+        pg = self._programs.get(key)
+        if pg is None or pg.device != device:
+            pg = self._build(side, chunk, device)
+            self._programs[key] = pg
+        return pg
+
+    # -- execution -------------------------------------------------------------
+    def run_chunk(self, pg: _Program, batch: int, logits_out: torch.Tensor, impl: Optional[int] = None) -> int:
+        """Run the program on the first `batch` frames staged in pg.in_buf; writes
+        logits_out (batch, out, V, V, V) f32.  Returns the number of kernels launched."""
+        assert batch <= pg.chunk and logits_out.is_contiguous() and logits_out.dtype == torch.float32
+        pg.buf_ptrs[pg.logits_buf] = C.c_void_p(logits_out.data_ptr())
+        if impl is not None:
+            for op in pg.op_array:
+                op.impl = impl
+        lib = _lib.load_library()
+        rc = lib.sceneego_v2v_run(pg.op_array, len(pg.ops), pg.buf_ptrs, C.c_void_p(pg.blob.data_ptr()), int(batch),
+                                  _lib._stream())
+        _lib._check(rc, "v2v_run")
+        return lib.sceneego_v2v_last_launch_count()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise _lib.SceneEgoError("V2VModel runs on CUDA only (no CPU fallback)")
+        b, c, side = x.shape[0], x.shape[1], x.shape[2]
+        assert c == self.input_channels
+        chunk = min(self.max_chunk, b)
+        pg = self.program(side, chunk, x.device)
+        out = torch.empty(b, self.output_channels, side, side, side, dtype=torch.float32, device=x.device)
+        x = x.contiguous().float()
+        for s in range(0, b, chunk):
+            n = min(chunk, b - s)
+            _lib.pack_volume(x[s:s + n], pg.buffers[pg.in_buf], pg.lay_in)
+            self.run_chunk(pg, n, out[s:s + n])
+        return out
+
+    def flops_per_frame(self, side: int) -> int:
+        """Algorithmic FLOPs of one frame (2*Cin*Cout*k^3 per output voxel)."""
+        total = 0
+        res = {"front_layers": side, "back_layers": side, "output_layer": side}
+        for name, m in self.named_modules():
+            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+                s = _side_of(name, side)
+                k = m.kernel_size[0]
+                if isinstance(m, nn.ConvTranspose3d):
+                    total += 2 * m.in_channels * m.out_channels * 8 * (s // 2) ** 3
+                else:
+                    total += 2 * m.in_channels * m.out_channels * k ** 3 * s ** 3
+        return total
+
+
+def _side_of(name: str, side: int) -> int:
+    """Spatial side of the OUTPUT of the conv called `name` inside V2VModel."""
+    if not name.startswith("encoder_decoder."):
+        return side
+    part = name.split(".")[1]
+    if part == "mid_res":
+        return side >> 5
+    lvl = int(part[-1])
+    if part.startswith("skip_res"):
+        return side >> (lvl - 1)
+    if part.startswith("encoder_res") or part.startswith("decoder_res"):
+        return side >> lvl
+    if part.startswith("decoder_upsample"):
+        return side >> (lvl - 1)
+    raise KeyError(name)

@@ -120,7 +120,7 @@ def main():
         idx = np.arange(0, V ** 3, 997)
         np.savez_compressed(os.path.join(OUT, f"tables_v{V}.npz"),
                             ray_idx=np.arange(0, t.ray.shape[0], 9973), ray=net.ray[::9973],
-                            ray_sum=net.ray.sum(0), vox_idx=idx,
+                            ray_xor=np.bitwise_xor.reduce(np.ascontiguousarray(net.ray).view(np.uint64), axis=0), vox_idx=idx,
                             grid_px=net.grid_coord_proj.numpy()[idx],
                             coord=net.coord_volume.reshape(-1, 3).numpy()[idx])
     report["tables"] = "exact"

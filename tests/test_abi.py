@@ -1,0 +1,51 @@
+"""CPU: the C-ABI library loads and exports every function include/sceneego_b200.h declares."""
+import ctypes
+import os
+import re
+
+from sceneego_b200 import _lib
+from tests import util
+
+
+def _declared():
+    src = open(os.path.join(util.ROOT, "include", "sceneego_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sceneego_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load_library()
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "python binding list out of sync with the header"
+    assert lib.sceneego_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Calib) == 8 * 20 + 8          # 20 doubles + 2 int32
+    assert ctypes.sizeof(_lib.VolLayout) == 32
+    assert ctypes.sizeof(_lib.V2VOp) == 10 * 4 + 16 + 2 * 32
+
+
+def test_host_only_entry_points():
+    lay = _lib.vol_layout(64, 1, 4)
+    assert (lay.pitch_y, lay.pitch_x) == (65, 4225)
+    assert lay.guard >= 4225 + 65 + 1 and lay.guard % 8 == 0 and lay.frame_pitch % 8 == 0
+    assert lay.plane_stride >= 4 * lay.frame_pitch + lay.guard + 1024
+    lay7 = _lib.vol_layout(64, 3, 1)
+    assert lay7.guard >= 3 * (67 * 67 + 67 + 1)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    import pytest
+    with pytest.raises(_lib.SceneEgoError, match="no CPU or PyTorch fallback"):
+        _lib.load_library(str(tmp_path / "nope.so"))
+
+
+def test_cpu_tensors_are_rejected():
+    import pytest
+    import torch
+    with pytest.raises(_lib.SceneEgoError):
+        _lib._ptr(torch.zeros(4))

@@ -1,0 +1,191 @@
+"""Tables, voxelisation (bit-exact) and unprojection (1e-3 relative) on the GPU, through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sceneego_oracle as orc
+from sceneego_b200.utils import synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cam():
+    from sceneego_b200.utils.fisheye.FishEyeCalibrated import FishEyeCameraCalibrated
+    return FishEyeCameraCalibrated(util.CALIB)
+
+
+@pytest.fixture(scope="module")
+def tables64():
+    return orc.StageTables(util.CALIB, 64, 2.0)
+
+
+def test_ray_table_bit_exact(cam, tables64):
+    ray = cam.ray_table_device(1280, 1024).cpu().numpy()           # (H, W, 3) row-major
+    ref = tables64.ray.reshape(1280, 1024, 3).transpose(1, 0, 2)   # oracle is x-major
+    assert np.array_equal(ray, ref)                                # every one of 1,310,720 pixels, fp64 bits
+    g = util.golden("tables_v64.npz")                              # vectors from the unmodified reference
+    flat = ray.transpose(1, 0, 2).reshape(-1, 3)
+    assert np.array_equal(flat[g["ray_idx"]], g["ray"])
+
+
+@pytest.mark.parametrize("V", [64, 128])
+def test_project_voxels(cam, V):
+    from sceneego_b200 import _lib
+    px, grid = _lib.project_voxels(cam.calib_struct(1280, 1024), V, 2.0, (1024, 1280), "cuda")
+    t = orc.StageTables(util.CALIB, V, 2.0)
+    # fp32 atan/sqrt differ from the CPU libm by an ulp or two: 1e-3 px on a 1280 px image
+    assert (px.cpu() - t.grid_px).abs().max().item() <= 1e-3
+    assert (grid.cpu() - t.grid.reshape(-1, 2)).abs().max().item() <= 2e-6
+    g = util.golden(f"tables_v{V}.npz")
+    assert np.abs(px.cpu().numpy()[g["vox_idx"]] - g["grid_px"]).max() <= 1e-3
+    # arbitrary-point entry agrees with the fused-coordinate entry
+    px2 = cam.world2camera_pytorch(t.coord_volume.reshape(-1, 3).cuda())
+    assert (px2 - px).abs().max().item() <= 1e-3
+
+
+def test_project_voxels_raises_on_axis(cam):
+    from sceneego_b200 import _lib
+    with pytest.raises(Exception, match="norm is zero"):
+        _lib.project_voxels(cam.calib_struct(1280, 1024), 33, 2.0, (1024, 1280), "cuda")   # odd V: voxel on the axis
+
+
+def _voxelize(cam, depth, V):
+    from sceneego_b200 import _lib
+    ray = cam.ray_table_device(1280, 1024)
+    d = torch.as_tensor(depth).float().cuda()
+    if d.dim() == 2:
+        d = d[None]
+    occ = torch.zeros(d.shape[0], V, V, V, device="cuda")
+    lay = _lib.vol_layout(V, 3, d.shape[0])
+    buf = _lib.alloc_volume(lay, 48, "cuda")
+    _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, 2.0, occ, buf, lay, channel=32)
+    planar = _lib.unpack_volume(buf, lay, d.shape[0], 40)[:, 32]
+    assert torch.equal(planar, occ), "planar bf16 scene channel differs from the f32 grid"
+    return occ.cpu().numpy()
+
+
+@pytest.mark.parametrize("V", [64, 128])
+def test_voxelize_demo_frames_bit_exact(cam, V):
+    g = util.golden("voxel.npz")
+    for name in ("img_001000", "img_001796", "img_002376"):
+        raw = g[f"{name}_raw"]
+        d = orc.resize_nearest(raw, 1024, 1280).copy()   # dataset/demo_dataset.py:86-91
+        d[d > 10] = 10
+        got = _voxelize(cam, d, V)[0]
+        ref = util.unpack_bits(g[f"{name}_v{V}"], V)
+        assert np.array_equal(got, ref), name
+        assert got[V // 2, V // 2, 0] == 1.0
+
+
+@pytest.mark.parametrize("V", [64, 128])
+def test_voxelize_synthetic_bit_exact(cam, tables64, V):
+    g = util.golden("voxel.npz")
+    cases = {"uniform": synth.synthetic_depth_uniform(1)[0].numpy(),
+             "room": synth.synthetic_depth_room(1, tables64.ray)[0].numpy(),
+             "uniform1024": synth.synthetic_depth_uniform(1, h=1024, w=1024)[0].numpy()}
+    for tag, d in cases.items():
+        assert np.array_equal(_voxelize(cam, d, V)[0], util.unpack_bits(g[f"{tag}_v{V}"], V)), tag
+
+
+def test_voxelize_edge_cases_vs_oracle(cam, tables64):
+    rng = np.random.default_rng(3)
+    cases = [np.zeros((1024, 1280), np.float32),                         # empty: only voxel (V/2,V/2,0)
+             np.full((1024, 1280), 10.0, np.float32),                    # clamp value everywhere
+             (rng.random((256, 320), dtype=np.float32) * 3),             # ragged small input, nearest upsample
+             (rng.random((1024, 1280), dtype=np.float32) * 6 - 1)]       # negative depths
+    weird = rng.random((1024, 1280), dtype=np.float32) * 2
+    weird[::7, ::5] = np.nan
+    weird[::11, ::3] = np.inf
+    cases.append(weird)
+    for d in cases:
+        ref = orc.voxelize_depth(d, tables64.ray, 64, 2.0)
+        assert np.array_equal(_voxelize(cam, d, 64)[0], ref)
+    assert _voxelize(cam, cases[0], 64)[0].sum() == 1.0
+
+
+def test_voxelize_batch_consistency_full_size(cam, tables64):
+    """BASELINE config sizes (B=64 frames of 1024x1280): frame i of a batch equals the frame alone,
+    every frame marks voxel (V/2,V/2,0), occupancy is {0,1}."""
+    d = torch.cat([synth.synthetic_depth_room(32, tables64.ray, seed=1), synth.synthetic_depth_uniform(32, seed=2)])
+    occ = _voxelize(cam, d, 64)
+    assert set(np.unique(occ)) <= {0.0, 1.0}
+    assert (occ[:, 32, 32, 0] == 1).all()
+    for i in (0, 31, 32, 63):
+        assert np.array_equal(occ[i], _voxelize(cam, d[i], 64)[0])
+    assert np.array_equal(occ[5], orc.voxelize_depth(d[5].numpy(), tables64.ray, 64, 2.0))
+
+
+def _pf(sd, feat):
+    return orc.process_features(feat, sd["process_features.0.weight"], sd["process_features.0.bias"])
+
+
+def test_unproject_vs_reference_golden(cam, tables64):
+    from sceneego_b200 import _lib
+    sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn")
+    feat = synth.synthetic_features(2)
+    w, b = sd["process_features.0.weight"].cuda(), sd["process_features.0.bias"].cuda()
+    feat32 = _lib.feature_conv1x1(feat.cuda(), w, b)
+    ref32 = torch.nn.functional.conv2d(feat, sd["process_features.0.weight"], sd["process_features.0.bias"])
+    assert (feat32.cpu().permute(0, 3, 1, 2) - ref32).abs().max().item() <= 1e-4 * ref32.abs().max().item()
+    g = util.golden("unproject_v64.npz")
+    ref = torch.from_numpy(g["lifted"])                      # from the unmodified reference
+    idx = torch.from_numpy(g["vox_idx"])
+    lay = _lib.vol_layout(64, 3, 2)
+    for fused in (False, True):
+        out = torch.empty(2, 32, 64, 64, 64, device="cuda")
+        buf = _lib.alloc_volume(lay, 48, "cuda")
+        grid = None if fused else tables64.grid.reshape(-1, 2).cuda().contiguous()
+        _lib.unproject(feat32, grid, cam.calib_struct(1280, 1024) if fused else None, 64, 2.0, 1024, 1280, out, buf,
+                       lay, extra_zero_planes=2)
+        got = out.reshape(2, 32, -1)[:, :, idx].cpu()
+        rel = ((got - ref).norm() / ref.norm()).item()
+        assert rel <= 1e-3, (fused, rel)                    # north-star tolerance
+        if not fused:
+            assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+        else:
+            assert torch.allclose(got, ref, rtol=1e-3, atol=2e-3)
+        planar = _lib.unpack_volume(buf, lay, 2, 48)
+        assert torch.equal(planar[:, :32], out.to(torch.bfloat16).float())   # same values, bf16-rounded
+        assert planar[:, 32:].abs().max().item() == 0.0
+
+
+def test_materialised_features_and_generic_grid_sample(tables64):
+    """Output #2 of the reference forward and the op-level drop-in: gathering from the
+    materialised 1024x1280 map with the generic kernel equals the fused gather (loop == batch)."""
+    from sceneego_b200 import _lib
+    from sceneego_b200.utils import op
+    sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn")
+    feat = synth.synthetic_features(2, seed=9)
+    feat32 = _lib.feature_conv1x1(feat.cuda(), sd["process_features.0.weight"].cuda(),
+                                  sd["process_features.0.bias"].cuda())
+    full = _lib.features_upsample_pad(feat32, 1024, 128)
+    ref_full = _pf(sd, feat)
+    assert full.shape == (2, 32, 1024, 1280)
+    assert (full.cpu() - ref_full).abs().max().item() <= 1e-4 * ref_full.abs().max().item()
+    grid_b = op.get_grid_coord_proj_batch(tables64.grid_px.cuda(), 4, (1024, 1280))
+    assert grid_b.shape == (4, 64 ** 3, 1, 2) and grid_b.stride(0) == 0
+    lifted = op.unproject_heatmaps_one_view_batch(full, grid_b, 64)
+    ref = orc.unproject(ref_full, tables64.grid.unsqueeze(0).expand(2, -1, -1, -1), 64)
+    # inputs differ by the 256-term fp32 summation order of the 1x1 conv (GPU vs CPU)
+    assert ((lifted.cpu() - ref).norm() / ref.norm()).item() <= 1e-5
+    assert torch.allclose(lifted.cpu(), ref, rtol=1e-3, atol=1e-3)
+    one = op.unproject_heatmaps_one_view(full[1:2], tables64.grid_px.cuda(), 64)
+    assert (one - lifted[1:2]).abs().sum().item() == 0.0     # the reference's own loop==batch smoke check
+    fused = torch.empty(2, 32, 64, 64, 64, device="cuda")
+    _lib.unproject(feat32, tables64.grid.reshape(-1, 2).cuda().contiguous(), None, 64, 2.0, 1024, 1280, fused, None, None)
+    assert torch.allclose(fused, lifted, rtol=1e-5, atol=1e-5)
+
+
+def test_generic_grid_sample_out_of_bounds():
+    from sceneego_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(2, 5, 37, 53, generator=g)
+    grid = (torch.rand(2, 4001, 1, 2, generator=g) * 2.6 - 1.3)          # 15% outside [-1,1]: zeros padding
+    ref = orc.grid_sample_bilinear(img, grid)
+    ref2 = torch.nn.functional.grid_sample(img, grid, align_corners=True).reshape(2, 5, -1)
+    assert torch.allclose(ref, ref2, atol=1e-5)
+    gd = grid.cuda().contiguous()
+    got = _lib.grid_sample(img.cuda(), gd, gd.stride(0))
+    assert torch.allclose(got.cpu(), ref, rtol=1e-5, atol=1e-5)

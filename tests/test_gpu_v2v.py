@@ -1,0 +1,164 @@
+"""V2V kernels vs torch fp32 (floating point -> tolerance stated per test)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_conv(cin, cout, k, seed, transposed=False):
+    g = torch.Generator().manual_seed(seed)
+    conv = (nn.ConvTranspose3d(cin, cout, 2, stride=2) if transposed
+            else nn.Conv3d(cin, cout, k, padding=(k - 1) // 2))
+    bn = nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * k ** 3)) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+        bn.weight.copy_(torch.rand(cout, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(cout, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(cout, generator=g) * 1.5 + 0.5)
+    return conv.cuda().eval(), bn.cuda().eval()
+
+
+def _ref(x, conv, bn, relu, res=None, add_after=None):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        y = bn(conv(x))
+        if res is not None:
+            y = y + res
+        if relu:
+            y = F.relu(y)
+        if add_after is not None:
+            y = y + add_after
+    return y
+
+
+def _close(got, ref, what):
+    # bf16 weights + bf16 output: 2^-8 relative per rounding; K up to 16k terms accumulate in fp32
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * scale + 1e-3, f"{what}: max abs err {err} vs scale {scale}"
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel <= 6e-3, f"{what}: relative Frobenius error {rel}"
+
+
+CASES = [
+    # (cin, cout, k, S, B, pad_src)
+    (32, 32, 3, 16, 2, 1),
+    (16, 32, 3, 16, 1, 1),
+    (32, 64, 3, 8, 3, 1),
+    (64, 64, 3, 16, 2, 1),
+    (64, 128, 3, 8, 2, 1),
+    (128, 128, 3, 8, 2, 1),
+    (128, 128, 3, 2, 2, 1),
+    (16, 32, 1, 16, 2, 1),
+    (32, 32, 1, 16, 2, 1),
+    (32, 15, 1, 16, 2, 1),
+    (33, 16, 7, 16, 2, 3),
+    (32, 32, 3, 64, 1, 1),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("cin,cout,k,S,B,pad_src", CASES)
+def test_single_conv(cin, cout, k, S, B, pad_src, impl):
+    conv, bn = _mk_conv(cin, cout, k, seed=cin * 1000 + cout * 10 + k)
+    g = torch.Generator().manual_seed(S + B)
+    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    res = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
+    got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=res, impl=impl, pad_src=pad_src)
+    _close(got, _ref(x, conv, bn, True, res=res), f"conv {cin}->{cout} k{k} S{S} impl{impl}")
+    # pad cells of the destination must be exactly zero (they are the next layer's padding)
+    full = dst.float().sum().item()
+    assert np.isfinite(full)
+    plane = dst[0].float()  # (plane_stride, 8)
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(S, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
+
+
+@pytest.mark.parametrize("cin,cout,S,B", [(32, 32, 16, 2), (128, 128, 4, 2), (16, 32, 32, 1)])
+def test_tc_matches_simt_bitwise_close(cin, cout, S, B):
+    """Same packed weights, same bf16 inputs: tensor-core and CUDA-core paths may differ only
+    by fp32 accumulation order, i.e. at most one bf16 ulp after the output rounding."""
+    conv, bn = _mk_conv(cin, cout, 3, seed=7)
+    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=torch.Generator().manual_seed(1))).cuda()
+    a, _, _ = util.run_single_op(x, conv, bn, relu=False, impl=0)
+    b, _, _ = util.run_single_op(x, conv, bn, relu=False, impl=1)
+    assert ((a - b).abs() <= 0.0079 * b.abs() + 1e-4).all()
+
+
+def test_maxpool_and_deconv():
+    from sceneego_b200 import _lib
+    import ctypes as C
+    S, B, c = 16, 2, 64
+    x = util.bf16_round(torch.randn(B, c, S, S, S, generator=torch.Generator().manual_seed(3))).cuda()
+    lay_s, lay_d = _lib.vol_layout(S, 1, B), _lib.vol_layout(S // 2, 1, B)
+    src, dst = _lib.alloc_volume(lay_s, c, x.device), _lib.alloc_volume(lay_d, c, x.device)
+    _lib.pack_volume(x, src, lay_s)
+    op = _lib.V2VOp()
+    op.type, op.cin, op.cout, op.cout_real, op.src, op.dst, op.res = _lib.OP_MAXPOOL2, c, c, c, 0, 1, -1
+    op.lay_src, op.lay_dst = lay_s, lay_d
+    ops = (_lib.V2VOp * 1)(op)
+    bufs = (C.c_void_p * 2)(src.data_ptr(), dst.data_ptr())
+    dummy = torch.zeros(16, device=x.device)
+    _lib._check(_lib.load_library().sceneego_v2v_run(ops, 1, bufs, C.c_void_p(dummy.data_ptr()), B, _lib._stream()),
+                "pool")
+    got = _lib.unpack_volume(dst, lay_d, B, c)
+    assert torch.equal(got, F.max_pool3d(x, 2, 2))          # exact: max of bf16 values
+
+    for cin, cout, s in ((64, 32, 8), (128, 128, 2), (128, 64, 4)):
+        conv, bn = _mk_conv(cin, cout, 2, seed=11, transposed=True)
+        x = util.bf16_round(torch.randn(B, cin, s, s, s, generator=torch.Generator().manual_seed(4))).cuda()
+        skip = util.bf16_round(torch.randn(B, cout, 2 * s, 2 * s, 2 * s, generator=torch.Generator().manual_seed(5))).cuda()
+        got, _, _ = util.run_single_op(x, conv, bn, relu=True, deconv=True, add_after=skip)
+        _close(got, _ref(x, conv, bn, True, add_after=skip), f"deconv {cin}->{cout}")
+
+
+@pytest.mark.parametrize("mode", ["default", "random_bn"])
+def test_v2v_v32_vs_reference_golden(mode):
+    """Whole V2V at V=32 against outputs of the UNMODIFIED reference (tests/golden/v2v_v32.npz).
+    Tolerance: bf16 activations through 52 layers -> 3% of the logit range, 1.5% Frobenius."""
+    from sceneego_b200.network.v2v import V2VModel
+    from sceneego_b200.utils import synth
+    m = V2VModel(33, 15).eval()
+    sd = synth.synthetic_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=1, mode=mode)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 33, 32, 32, 32, generator=g).abs()
+    x[:, 32] = (x[:, 32] > 1.0).float()
+    with torch.no_grad():
+        out = m(x.cuda())
+    ref = torch.from_numpy(util.golden("v2v_v32.npz")[mode])
+    got = out.reshape(15, -1)[:, ::13].cpu()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 3e-2 * scale
+    assert ((got - ref).norm() / ref.norm()).item() <= 1.5e-2
+
+
+def test_v2v_simt_and_tc_whole_network_agree():
+    from sceneego_b200.network.v2v import V2VModel
+    torch.manual_seed(0)
+    m = V2VModel(33, 15).eval().cuda()
+    x = torch.randn(2, 33, 32, 32, 32, device="cuda").abs()
+    pg = m.program(32, 2, x.device)
+    from sceneego_b200 import _lib
+    _lib.pack_volume(x, pg.buffers[pg.in_buf], pg.lay_in)
+    a = torch.empty(2, 15, 32, 32, 32, device="cuda")
+    b = torch.empty_like(a)
+    m.run_chunk(pg, 2, a, impl=0)
+    m.run_chunk(pg, 2, b, impl=1)
+    m.run_chunk(pg, 2, a, impl=0)   # again: buffers reused, pads must still be clean
+    torch.cuda.synchronize()
+    assert ((a - b).norm() / b.norm()).item() <= 2e-2   # accumulation order x 52 bf16-rounded layers

@@ -1,0 +1,82 @@
+"""CPU: the oracle restatement vs vectors produced by the UNMODIFIED reference
+(tests/make_golden.py, run in the build container).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sceneego_oracle as orc
+from sceneego_b200.utils import synth
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def tabs():
+    return {V: orc.StageTables(util.CALIB, V, 2.0) for V in (64, 128)}
+
+
+@pytest.mark.parametrize("V", [64, 128])
+def test_tables(tabs, V):
+    g, t = util.golden(f"tables_v{V}.npz"), tabs[V]
+    assert np.array_equal(t.ray[g["ray_idx"]], g["ray"])                 # fp64, bit-exact
+    assert np.array_equal(np.bitwise_xor.reduce(np.ascontiguousarray(t.ray).view(np.uint64), axis=0), g["ray_xor"])  # order-free checksum of all 1,310,720 rays
+    assert np.array_equal(t.grid_px.numpy()[g["vox_idx"]], g["grid_px"])
+    assert np.array_equal(t.coord_volume.reshape(-1, 3).numpy()[g["vox_idx"]], g["coord"])
+
+
+def test_world2camera_raises_on_axis():
+    calib = orc.load_calibration(util.CALIB)
+    with pytest.raises(Exception, match="norm is zero"):
+        orc.world2camera_f32(calib, orc.build_coord_volume(33, 2.0).reshape(-1, 3))
+
+
+@pytest.mark.parametrize("V", [64, 128])
+def test_voxel_occupancy_bit_exact(tabs, V):
+    g = util.golden("voxel.npz")
+    counts = {}
+    for name in ("img_001000", "img_001796", "img_002376"):
+        d = orc.resize_nearest(g[f"{name}_raw"], 1024, 1280).copy()
+        d[d > 10] = 10
+        got = orc.voxelize_depth(d, tabs[V].ray, V, 2.0)
+        assert np.array_equal(got, util.unpack_bits(g[f"{name}_v{V}"], V))
+        counts[name] = int(got.sum())
+    if V == 64:   # fingerprints recorded by the survey
+        assert counts == {"img_001000": 8331, "img_001796": 6787, "img_002376": 7450}
+    d = synth.synthetic_depth_uniform(1, h=1024, w=1024)[0].numpy()
+    assert np.array_equal(orc.voxelize_depth(d, tabs[V].ray, V, 2.0), util.unpack_bits(g[f"uniform1024_v{V}"], V))
+
+
+def test_unproject(tabs):
+    g = util.golden("unproject_v64.npz")
+    sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn")
+    pf = orc.process_features(synth.synthetic_features(2), sd["process_features.0.weight"],
+                              sd["process_features.0.bias"])
+    assert pf.shape == (2, 32, 1024, 1280) and float(pf[..., :128].abs().max()) == 0.0
+    lifted = orc.unproject(pf, tabs[64].grid.unsqueeze(0).expand(2, -1, -1, -1), 64)
+    got = lifted.reshape(2, 32, -1)[:, :, g["vox_idx"]].numpy()
+    assert np.abs(got - g["lifted"]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("mode", ["default", "random_bn"])
+def test_v2v(mode):
+    g = util.golden("v2v_v32.npz")
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 33, 32, 32, 32, generator=gen).abs()
+    x[:, 32] = (x[:, 32] > 1.0).float()
+    shapes = [(k[len("volume_net."):], s) for k, s in util.manifest() if k.startswith("volume_net.")]
+    sd = synth.synthetic_state_dict(shapes, seed=1, mode=mode)
+    with torch.no_grad():
+        out = orc.v2v_forward(sd, x)
+    assert np.abs(out.reshape(15, -1)[:, ::13].numpy() - g[mode]).max() <= 1e-5
+
+
+def test_stage_end_to_end(tabs):
+    g = util.golden("stage_v64.npz")
+    sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn", logit_scale=30.0)
+    feat = synth.synthetic_features(2)
+    depth = torch.cat([synth.synthetic_depth_room(1, tabs[64].ray), synth.synthetic_depth_uniform(1)])
+    with torch.no_grad():
+        kp, _, vol, inter = orc.stage_forward(tabs[64], sd, feat, depth_batch=depth, return_intermediates=True)
+    assert orc.mpjpe(kp.numpy(), g["kp_random_bn_s30"]) <= 5e-5          # metres: fp32 summation order only
+    assert np.allclose(inter["logits"].reshape(2, 15, -1)[:, :, ::257].numpy(), g["logits_random_bn_s30"],
+                       rtol=1e-4, atol=1e-4)
+    assert float(inter["scene"][:, 32, 32, 0].min()) == 1.0

@@ -1,0 +1,82 @@
+"""Shared helpers for the test-suite (checker side: may import oracle/)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CALIB = os.path.join(ROOT, "sceneego_b200", "data", "fisheye.calibration_05_08.json")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def manifest():
+    return [(k, tuple(s)) for k, s in json.load(open(os.path.join(GOLDEN, "state_dict_manifest.json")))]
+
+
+def stage_shapes():
+    return [(k, s) for k, s in manifest() if not k.startswith("backbone.")]
+
+
+def load_config(batch_size=4, volume_size=64):
+    from sceneego_b200 import DEFAULT_CONFIG
+    from sceneego_b200.utils import cfg
+    c = cfg.load_config(DEFAULT_CONFIG)
+    c.opt.batch_size = batch_size
+    c.model.volume_size = volume_size
+    return c
+
+
+def unpack_bits(packed, V):
+    return np.unpackbits(packed)[: V ** 3].reshape(V, V, V).astype(np.float32)
+
+
+def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None):
+    """Run one V2V op (conv or deconv) through sceneego_v2v_run; x (B,Cin,S,S,S) f32 cuda."""
+    from sceneego_b200 import _lib
+    from sceneego_b200.network.v2v import _Program, _pad16
+    B, cin, S = x.shape[0], x.shape[1], x.shape[2]
+    pg = _Program.__new__(_Program)
+    pg.side, pg.chunk, pg.device = S, B, x.device
+    pg.ops, pg.buffers, pg.buf_level, pg.free, pg.blob_parts, pg.blob_bytes = [], [], [], {}, [], 0
+    pg.flops = 0
+    So = 2 * S if deconv else S
+    lay_s = _lib.vol_layout(S, pad_src, B)
+    lay_d = _lib.vol_layout(So, 1, B)
+    cin_p, cout_p = _pad16(cin), _pad16(conv.out_channels)
+    src = _lib.alloc_volume(lay_s, cin_p, x.device)
+    dst = _lib.alloc_volume(lay_d, cout_p, x.device)
+    _lib.pack_volume(x.contiguous(), src, lay_s)
+    bufs = [src, dst]
+    lays = [lay_s, lay_d]
+    r_idx = -1
+    extra = res if res is not None else add_after
+    if extra is not None:
+        rb = _lib.alloc_volume(lay_d, cout_p, x.device)
+        _lib.pack_volume(extra.contiguous(), rb, lay_d)
+        bufs.append(rb)
+        lays.append(lay_d)
+        r_idx = 2
+    pg.buffers = bufs
+    pg.buf_level = [0] * len(bufs)
+    pg.lay_of = lambda i: lays[i]
+    if deconv:
+        pg.deconv(conv, bn, 0, 1, add=r_idx)
+    else:
+        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx)
+    pg.ops[0].impl = impl
+    pg.finalize()
+    lib = _lib.load_library()
+    rc = lib.sceneego_v2v_run(pg.op_array, 1, pg.buf_ptrs, C.c_void_p(pg.blob.data_ptr()), B, _lib._stream())
+    _lib._check(rc, "v2v_run")
+    torch.cuda.synchronize()
+    return _lib.unpack_volume(dst, lay_d, B, conv.out_channels), dst, lay_d
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
