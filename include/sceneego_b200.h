@@ -191,6 +191,12 @@ int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const flo
 int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,
                      int batch, void* stream);
 
+/* Measurement variant of sceneego_v2v_run: brackets every op with CUDA events on `stream`,
+ * waits for them (the only entry point that synchronises) and returns per-op milliseconds
+ * in h_ms[n_ops].  Used by bench.py for the per-kernel roofline. */
+int sceneego_v2v_run_profile(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers,
+                             const void* d_blob, int batch, void* stream, float* h_ms);
+
 /* Number of kernels the last sceneego_v2v_run on this thread launched. */
 int sceneego_v2v_last_launch_count(void);
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "sceneego_abi_version", "sceneego_last_error", "sceneego_ray_table_f64", "sceneego_project_voxels_f32",
     "sceneego_feature_conv1x1_f32", "sceneego_features_upsample_pad_f32", "sceneego_vol_layout_make",
     "sceneego_unproject_f32", "sceneego_voxelize_depth_f64", "sceneego_pack_volume_bf16",
-    "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run",
+    "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32",
 ]

@@ -119,7 +119,6 @@ struct ConvParams {
   uint32_t win_bytes, wchunk_bytes, tap_bytes;
   uint32_t off_win, off_w, off_bias, off_bar;
   uint32_t tmem_cols, half_cols;
-  int swap_lbo_sbo;                 // debug switch for descriptor-field validation
 };
 
 constexpr int CONV_THREADS = 192;
@@ -280,10 +279,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=p.N
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
-      const uint32_t a_lbo = p.swap_lbo_sbo ? 128u : p.win_bytes;
-      const uint32_t a_sbo = p.swap_lbo_sbo ? p.win_bytes : 128u;
-      const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.N * 16u;
-      const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)p.N * 16u : 128u;
+      // K-major no-swizzle: LBO = byte stride between the two 8-channel K chunks of one MMA,
+      // SBO = byte stride between 8-row core matrices (validated on B200 hardware)
+      const uint32_t a_lbo = p.win_bytes, a_sbo = 128u;
+      const uint32_t b_lbo = (uint32_t)p.N * 16u, b_sbo = 128u;
       int ws = 0, wph = 0, sl = 0, sph = 0;
       for (int it = 0; it < my_items; ++it) {
         const int buf = it & 1;
@@ -567,8 +566,8 @@ extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias
   return SCENEEGO_OK;
 }
 
-extern "C" int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,
-                                int batch, void* stream) {
+static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,
+                        int batch, void* stream, cudaEvent_t* ev) {
   SE_REQUIRE(ops && d_buffers && d_blob && n_ops > 0 && batch > 0, "v2v_run: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
@@ -577,10 +576,10 @@ extern "C" int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* c
     if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
     attr_set = true;
   }
-  const char* swap_env = getenv("SCENEEGO_SWAP_LBO_SBO");
   const char* force_simt = getenv("SCENEEGO_FORCE_SIMT");
   g_launches = 0;
   for (int i = 0; i < n_ops; ++i) {
+    if (ev) cudaEventRecord(ev[i], st);
     const sceneego_v2v_op_t& op = ops[i];
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -629,11 +628,34 @@ extern "C" int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* c
     const int smem = plan_conv(p);
     SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", i);
     p.n_items = (int)((n_pos + p.L - 1) / p.L);
-    p.swap_lbo_sbo = swap_env ? atoi(swap_env) : 0;
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
     conv_tc_kernel<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
     SE_CUDA_LAUNCH_CHECK("conv_tc");
     ++g_launches;
   }
+  if (ev) cudaEventRecord(ev[n_ops], st);
   return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,
+                                int batch, void* stream) {
+  return v2v_run_impl(ops, n_ops, d_buffers, d_blob, batch, stream, nullptr);
+}
+
+// Measurement variant: brackets every op with CUDA events on `stream`, waits for the stream and
+// returns per-op milliseconds in h_ms[n_ops].  (The only entry point that synchronises.)
+extern "C" int sceneego_v2v_run_profile(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers,
+                                        const void* d_blob, int batch, void* stream, float* h_ms) {
+  SE_REQUIRE(h_ms && n_ops > 0 && n_ops < 4096, "v2v_run_profile: bad argument");
+  cudaEvent_t* ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * (n_ops + 1));
+  for (int i = 0; i <= n_ops; ++i) cudaEventCreate(&ev[i]);
+  int rc = v2v_run_impl(ops, n_ops, d_buffers, d_blob, batch, stream, ev);
+  if (rc == SCENEEGO_OK) {
+    cudaError_t e = cudaEventSynchronize(ev[n_ops]);
+    if (e != cudaSuccess) { set_error("v2v_run_profile: %s", cudaGetErrorString(e)); rc = SCENEEGO_E_CUDA; }
+    for (int i = 0; i < n_ops && rc == SCENEEGO_OK; ++i) cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+  }
+  for (int i = 0; i <= n_ops; ++i) cudaEventDestroy(ev[i]);
+  free(ev);
+  return rc;
 }

@@ -106,6 +106,7 @@ class _Program:
         self.in_buf = self._new_buffer(-1)
         self.logits_buf: Optional[int] = None
         self.flops = 0
+        self.meta: List[dict] = []      # per op: kind, real channels, kernel size, side, algorithmic flops/frame
 
     # -- buffers -------------------------------------------------------------
     def _new_buffer(self, level: int) -> int:
@@ -180,7 +181,10 @@ class _Program:
         op.lay_src = self.lay_of(src)
         op.lay_dst = self.lay_of(dst) if not out_f32 else self.lay_of(src)
         self.ops.append(op)
-        self.flops += 2 * conv.in_channels * conv.out_channels * k ** 3 * op.lay_src.side ** 3
+        fl = 2 * conv.in_channels * conv.out_channels * k ** 3 * op.lay_src.side ** 3
+        self.flops += fl
+        self.meta.append(dict(kind="conv", cin=conv.in_channels, cout=conv.out_channels, k=k,
+                              side=op.lay_src.side, flops=fl))
 
     def pool(self, src: int, dst: int, channels: int):
         op = _lib.V2VOp()
@@ -188,6 +192,7 @@ class _Program:
         op.src, op.dst, op.res = src, dst, -1
         op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
         self.ops.append(op)
+        self.meta.append(dict(kind="pool", cin=channels, cout=channels, k=2, side=op.lay_src.side, flops=0))
 
     def deconv(self, conv: nn.ConvTranspose3d, bn, src: int, dst: int, add: int):
         cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
@@ -200,7 +205,10 @@ class _Program:
         op.w_offset, op.b_offset = w_off, b_off
         op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
         self.ops.append(op)
-        self.flops += 2 * conv.in_channels * conv.out_channels * 8 * op.lay_src.side ** 3
+        fl = 2 * conv.in_channels * conv.out_channels * 8 * op.lay_src.side ** 3
+        self.flops += fl
+        self.meta.append(dict(kind="deconv", cin=conv.in_channels, cout=conv.out_channels, k=2,
+                              side=op.lay_src.side, flops=fl))
 
     def finalize(self):
         self.blob = torch.from_numpy(np.concatenate(self.blob_parts)).to(self.device)
@@ -327,6 +335,15 @@ class V2VModel(nn.Module):
                                   _lib._stream())
         _lib._check(rc, "v2v_run")
         return lib.sceneego_v2v_last_launch_count()
+
+    def profile_chunk(self, pg: _Program, batch: int, logits_out: torch.Tensor):
+        """Like run_chunk but returns [(op, milliseconds)] measured with CUDA events per op."""
+        pg.buf_ptrs[pg.logits_buf] = C.c_void_p(logits_out.data_ptr())
+        ms = (C.c_float * len(pg.ops))()
+        rc = _lib.load_library().sceneego_v2v_run_profile(pg.op_array, len(pg.ops), pg.buf_ptrs,
+                                                          C.c_void_p(pg.blob.data_ptr()), int(batch), _lib._stream(), ms)
+        _lib._check(rc, "v2v_run_profile")
+        return [(pg.meta[i], float(ms[i])) for i in range(len(pg.ops))]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:

@@ -1,0 +1,62 @@
+"""Host-facing front end of the stage: pinned host buffers in, poses on the host out.
+
+`HostStagePipeline.run(batches)` is the end-to-end call a `demo.py`/`test.py`-style
+loop makes once the backbone features and depth maps live in host memory: every
+batch is copied host->device on a side stream (double-buffered, so the copy of
+batch i+1 overlaps the kernels of batch i), lifted with
+`VoxelNetwork_depth.lift`, and its (B,15,3) poses are copied back.
+"""
+from typing import Iterable, List, Tuple
+
+import torch
+
+
+class HostStagePipeline:
+    def __init__(self, net, gather_fn=None):
+        self.net = net
+        self.device = torch.device(net.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.gather_fn = gather_fn
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _stage(self, slot: int, feat: torch.Tensor, depth: torch.Tensor) -> None:
+        if not (feat.is_pinned() and depth.is_pinned()):
+            raise ValueError("HostStagePipeline needs pinned host tensors")
+        if self.slots[slot] is None or self.slots[slot][0].shape != feat.shape or self.slots[slot][1].shape != depth.shape:
+            self.slots[slot] = (torch.empty(feat.shape, dtype=torch.float32, device=self.device),
+                                torch.empty(depth.shape, dtype=torch.float32, device=self.device))
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[slot])          # slot's previous consumer finished
+            self.slots[slot][0].copy_(feat, non_blocking=True)
+            self.slots[slot][1].copy_(depth, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.h2d_bytes += feat.numel() * 4 + depth.numel() * 4
+
+    def run(self, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> List[torch.Tensor]:
+        batches = list(batches)
+        out = []
+        main = torch.cuda.current_stream(self.device)
+        if batches:
+            self._stage(0, *batches[0])
+        for i in range(len(batches)):
+            slot = i & 1
+            if i + 1 < len(batches):
+                self._stage(slot ^ 1, *batches[i + 1])
+            main.wait_event(self.ready[slot])
+            feat, depth = self.slots[slot]
+            with torch.no_grad():
+                kp = self.net.lift(feat, self.net.grid_coord_proj_batch, self.net.coord_volumes,
+                                   depth_map_batch=depth)[0]
+            if self.gather_fn is not None:
+                kp = self.gather_fn(kp)
+            self.done[slot].record(main)
+            host = torch.empty(kp.shape, dtype=kp.dtype, pin_memory=True)
+            host.copy_(kp, non_blocking=True)
+            self.d2h_bytes += kp.numel() * 4
+            out.append(host)
+        main.synchronize()
+        return out

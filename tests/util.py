@@ -45,6 +45,7 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     pg.side, pg.chunk, pg.device = S, B, x.device
     pg.ops, pg.buffers, pg.buf_level, pg.free, pg.blob_parts, pg.blob_bytes = [], [], [], {}, [], 0
     pg.flops = 0
+    pg.meta = []
     So = 2 * S if deconv else S
     lay_s = _lib.vol_layout(S, pad_src, B)
     lay_d = _lib.vol_layout(So, 1, B)
