@@ -65,10 +65,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Warp-converged variant: the loop condition is a warp vote, so control flow stays uniform and
+// ptxas keeps the MMA issuer's descriptor arithmetic in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (++spins > (1u << 26)) __trap();   // protocol bug: fail loudly instead of hanging the GPU
+  }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -169,9 +186,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return *reinterpret_cast<const uint4*>(h);
 }
 
-// Shared epilogue: v[0..15] are output channels c0..c0+15 of one row.
-__device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& ri, int c0, float (&v)[16],
-                                            const float* s_bias) {
+// Shared epilogue: v[0..15] are output channels c0..c0+15 of one row; r0/r1 hold the residual
+// cells (8 channels each) already loaded by the caller (ignored unless a residual flag is set).
+__device__ __forceinline__ void store_row16_pre(const ConvParams& p, const RowInfo& ri, int c0, float (&v)[16],
+                                                const float* s_bias, const uint4& r0, const uint4& r1) {
   if (!ri.write) return;
   const int S = p.ls.side;
   if (p.flags & SCENEEGO_F_OUT_F32) {
@@ -194,8 +212,7 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& 
     const int64_t cell = (int64_t)((c0 >> 3) + g) * p.ld.plane_stride + ri.dpos;
     if (ri.valid) {
       float rr[8];
-      const bool has_res = (p.flags & (SCENEEGO_F_RESIDUAL | SCENEEGO_F_ADD_AFTER)) != 0;
-      if (has_res) unpack8(*reinterpret_cast<const uint4*>(p.res + cell * 8), rr);
+      unpack8(g ? r1 : r0, rr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = v[8 * g + j] + s_bias[c0 + 8 * g + j];
@@ -212,12 +229,37 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& 
   }
 }
 
+// Residual cells of channels c0..c0+15 of one row (zeros when the op has no residual).
+__device__ __forceinline__ void load_res16(const ConvParams& p, const RowInfo& ri, int c0, uint4& r0, uint4& r1) {
+  r0 = make_uint4(0, 0, 0, 0);
+  r1 = r0;
+  if ((p.flags & (SCENEEGO_F_RESIDUAL | SCENEEGO_F_ADD_AFTER)) && ri.valid && !(p.flags & SCENEEGO_F_OUT_F32)) {
+    const int64_t cell = (int64_t)(c0 >> 3) * p.ld.plane_stride + ri.dpos;
+    r0 = *reinterpret_cast<const uint4*>(p.res + cell * 8);
+    r1 = *reinterpret_cast<const uint4*>(p.res + (cell + p.ld.plane_stride) * 8);
+  }
+}
+
+__device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& ri, int c0, float (&v)[16],
+                                            const float* s_bias) {
+  uint4 r0, r1;
+  load_res16(p, ri, c0, r0, r1);
+  store_row16_pre(p, ri, c0, v, s_bias, r0, r1);
+}
+
 // ---------------------------------------------------------------------------
-// tcgen05 implicit-GEMM conv
+// tcgen05 implicit-GEMM conv.  KSTEPS = Cin/16 and TILES = 128-row tiles per work item are
+// compile-time so that the per-tap block of TILES*KSTEPS MMAs is straight-line code whose
+// descriptors differ by constants: the single issuing lane must sustain one tcgen05.mma per
+// ~41 cycles (measured floor at N<=32, tools/mma_rate.cu).
 // ---------------------------------------------------------------------------
+template <int KSTEPS, int TILES>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are
+  // uniform branches and the MMA issuer's address arithmetic can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -248,19 +290,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 
   const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int halo = p.r * (p.ls.pitch_y + 1);   // window starts `halo` positions before the item
+  constexpr int L = TILES * 128;
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
       int ws = 0, wph = 0, sl = 0, sph = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * p.L;
+        const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * L;
         for (int dx = 0; dx < p.k; ++dx) {
           mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
-          mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * p.cin_planes);
+          mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * (2 * KSTEPS));
           const int64_t qs = q0 + (int64_t)(dx - p.r) * p.ls.pitch_x - halo;
-          for (int g = 0; g < p.cin_planes; ++g)
-            bulk_g2s(sbase + p.off_win + (uint32_t)(ws * p.cin_planes + g) * p.win_bytes,
+#pragma unroll
+          for (int g = 0; g < 2 * KSTEPS; ++g)
+            bulk_g2s(sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS + g) * p.win_bytes,
                      p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8, p.win_bytes, BAR(B_FULL_WIN + ws));
           if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
           for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
@@ -276,72 +320,97 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=p.N
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
-      // K-major no-swizzle: LBO = byte stride between the two 8-channel K chunks of one MMA,
-      // SBO = byte stride between 8-row core matrices (validated on B200 hardware)
-      const uint32_t a_lbo = p.win_bytes, a_sbo = 128u;
-      const uint32_t b_lbo = (uint32_t)p.N * 16u, b_sbo = 128u;
-      int ws = 0, wph = 0, sl = 0, sph = 0;
-      for (int it = 0; it < my_items; ++it) {
-        const int buf = it & 1;
-        mbar_wait(BAR(B_TMEM_EMPTY + buf), ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)buf * p.half_cols;
-        uint32_t acc = 0;
-        for (int dx = 0; dx < p.k; ++dx) {
-          mbar_wait(BAR(B_FULL_WIN + ws), wph);
-          const uint32_t win = sbase + p.off_win + (uint32_t)(ws * p.cin_planes) * p.win_bytes;
-          for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
-            mbar_wait(BAR(B_FULL_W + sl), sph);
-            tc_fence_after();
-            const uint32_t wsm = sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes;
-            for (int tt = 0; tt < p.wchunk_taps; ++tt) {
-              const int tap = wc * p.wchunk_taps + tt;     // index inside this dx: dy*k + dz
-              const int dy = tap / p.k, dz = tap - dy * p.k;
-              const uint32_t rowoff = (uint32_t)(dy * p.ls.pitch_y + dz) * 16u;
-              for (int t = 0; t < p.tiles; ++t) {
-                for (int ks = 0; ks < p.ksteps; ++ks) {
-                  const uint64_t ad = make_desc(win + rowoff + (uint32_t)t * 2048u + (uint32_t)(2 * ks) * p.win_bytes,
-                                                a_lbo, a_sbo);
-                  const uint64_t bd = make_desc(wsm + (uint32_t)tt * p.tap_bytes + (uint32_t)(2 * ks) * (uint32_t)p.N * 16u,
-                                                b_lbo, b_sbo);
-                  tc_mma_bf16(d0 + (uint32_t)(t * p.N), ad, bd, idesc, acc | (uint32_t)ks);
-                }
-              }
-              acc = 1;
-            }
-            tc_commit(BAR(B_EMPTY_W + sl));
-            if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
-          }
-          tc_commit(BAR(B_EMPTY_WIN + ws));
-          if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
-        }
-        tc_commit(BAR(B_TMEM_FULL + buf));
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // The whole warp runs this loop converged so that every descriptor is a warp-uniform value
+    // (uniform registers, no per-MMA R2UR/ELECT loop); only the tcgen05 instructions themselves
+    // are predicated on one elected lane, which is also the lane that commits.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const bool leader = elect_one();
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=p.N
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
+    // K-major no-swizzle: LBO = byte stride between the two 8-channel K chunks of one MMA,
+    // SBO = byte stride between 8-row core matrices (validated on B200 hardware).
+    // hi word: SBO = 128 B (>>4 = 8) | descriptor version 1 (bit 46 -> bit 14 of the hi word)
+    const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
+    const uint32_t a_lo_flags = ((p.win_bytes >> 4) & 0x3FFFu) << 16;          // LBO = window plane stride
+    const uint32_t b_lo_flags = (((uint32_t)p.N * 16u >> 4) & 0x3FFFu) << 16;  // LBO = Cout * 16 B
+    const uint32_t a_ks_step = (2u * p.win_bytes) >> 4;                        // two planes per K step
+    const uint32_t b_ks_step = (2u * (uint32_t)p.N * 16u) >> 4;
+    const uint32_t b_tap_step = p.tap_bytes >> 4;
+    const uint32_t n_cols = (uint32_t)p.N;
+    const int pitch_y = p.ls.pitch_y, ksz = p.k, wtaps = p.wchunk_taps;
+    int ws = 0, wph = 0, sl = 0, sph = 0;
     for (int it = 0; it < my_items; ++it) {
       const int buf = it & 1;
-      const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * p.L;
+      mbar_wait_warp(BAR(B_TMEM_EMPTY + buf), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_u + (uint32_t)buf * p.half_cols;
+      uint32_t acc = 0;
+      for (int dx = 0; dx < ksz; ++dx) {
+        mbar_wait_warp(BAR(B_FULL_WIN + ws), wph);
+        const uint32_t win_lo = (((sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS) * p.win_bytes) >> 4) & 0x3FFFu) |
+                                a_lo_flags;
+        int dy = 0, dz = 0;
+        for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
+          mbar_wait_warp(BAR(B_FULL_W + sl), sph);
+          tc_fence_after();
+          uint32_t b_lo = (((sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes) >> 4) & 0x3FFFu) | b_lo_flags;
+          for (int tt = 0; tt < wtaps; ++tt) {
+            const uint32_t a_lo = win_lo + (uint32_t)(dy * pitch_y + dz);      // tap shift, in 16-B cells
+            if (leader) {
+#pragma unroll
+              for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks)
+                  tc_mma_bf16(d0 + (uint32_t)t * n_cols, desc_hi | (a_lo + (uint32_t)t * 128u + (uint32_t)ks * a_ks_step),
+                              desc_hi | (b_lo + (uint32_t)ks * b_ks_step), idesc, ks == 0 ? acc : 1u);
+              }
+            }
+            acc = 1;
+            b_lo += b_tap_step;
+            if (++dz == ksz) { dz = 0; ++dy; }
+          }
+          if (leader) tc_commit(BAR(B_EMPTY_W + sl));
+          if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+        }
+        if (leader) tc_commit(BAR(B_EMPTY_WIN + ws));
+        if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+      }
+      if (leader) tc_commit(BAR(B_TMEM_FULL + buf));
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    // Chunks of 16 output channels; the residual cells of chunk i+1 are requested before chunk i
+    // is processed so that their global-load latency overlaps the TMEM read and the math.
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int nch = p.N >> 4;
+    for (int it = 0; it < my_items; ++it) {
+      const int buf = it & 1;
+      const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * L;
+      RowInfo ri = decode_row(p, q0 + quarter * 32 + lane);
+      uint4 rn0, rn1;
+      load_res16(p, ri, 0, rn0, rn1);
       mbar_wait(BAR(B_TMEM_FULL + buf), (it >> 1) & 1);
       tc_fence_after();
-      for (int t = 0; t < p.tiles; ++t) {
-        const RowInfo ri = decode_row(p, q0 + t * 128 + quarter * 32 + lane);
+#pragma unroll 1
+      for (int t = 0; t < TILES; ++t) {
+        RowInfo ri_next = ri;
+        if (t + 1 < TILES) ri_next = decode_row(p, q0 + (t + 1) * 128 + quarter * 32 + lane);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * p.half_cols +
                                (uint32_t)(t * p.N);
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
+        for (int c = 0; c < nch; ++c) {
+          const uint4 r0 = rn0, r1 = rn1;
+          if (c + 1 < nch) load_res16(p, ri, (c + 1) << 4, rn0, rn1);
+          else if (t + 1 < TILES) load_res16(p, ri_next, 0, rn0, rn1);
           uint32_t raw[16];
-          tc_ld16(taddr + (uint32_t)c0, raw);
+          tc_ld16(taddr + (uint32_t)(c << 4), raw);
           tc_wait_ld();
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-          store_row16(p, ri, c0, v, s_bias);
+          store_row16_pre(p, ri, c << 4, v, s_bias, r0, r1);
         }
+        ri = ri_next;
       }
       tc_fence_before();
       __syncwarp();
@@ -353,6 +422,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+}
+
+typedef void (*conv_tc_fn)(const ConvParams);
+static conv_tc_fn pick_conv_tc(int ksteps, int tiles) {
+#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T>;
+  SE_CASE(1, 8) SE_CASE(2, 8) SE_CASE(3, 4) SE_CASE(3, 8) SE_CASE(2, 4) SE_CASE(4, 4) SE_CASE(4, 2) SE_CASE(8, 2)
+  SE_CASE(1, 4) SE_CASE(1, 2) SE_CASE(2, 2) SE_CASE(8, 1) SE_CASE(4, 1) SE_CASE(2, 1) SE_CASE(1, 1) SE_CASE(3, 2) SE_CASE(3, 1)
+#undef SE_CASE
+  return nullptr;
 }
 
 // ---------------------------------------------------------------------------
@@ -570,12 +648,6 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
                         int batch, void* stream, cudaEvent_t* ev) {
   SE_REQUIRE(ops && d_buffers && d_blob && n_ops > 0 && batch > 0, "v2v_run: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-    attr_set = true;
-  }
   const char* force_simt = getenv("SCENEEGO_FORCE_SIMT");
   g_launches = 0;
   for (int i = 0; i < n_ops; ++i) {
@@ -629,7 +701,20 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
     SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", i);
     p.n_items = (int)((n_pos + p.L - 1) / p.L);
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-    conv_tc_kernel<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
+    conv_tc_fn fn = pick_conv_tc(p.ksteps, p.tiles);
+    SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d", i, p.ksteps, p.tiles);
+    {
+      static conv_tc_fn configured[32];
+      static int n_configured = 0;
+      bool done = false;
+      for (int c = 0; c < n_configured; ++c) done |= (configured[c] == fn);
+      if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+        if (n_configured < 32) configured[n_configured++] = fn;
+      }
+    }
+    fn<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
     SE_CUDA_LAUNCH_CHECK("conv_tc");
     ++g_launches;
   }
