@@ -174,6 +174,8 @@ typedef struct sceneego_v2v_op {
   int32_t cout_real;   /* channels actually written (15 for the output layer)             */
   int32_t src, dst, res;  /* buffer indices (res = -1 if unused)                           */
   int32_t impl;        /* 0 = tcgen05 implicit GEMM, 1 = CUDA-core checker kernel          */
+  int32_t xstack;      /* conv: GEMM rows produce `xstack` consecutive x-planes (N = xstack*cout),
+                          weights packed with the same xstack; 0/1 = off                    */
   int64_t w_offset;    /* byte offset of the packed bf16 weights in the blob               */
   int64_t b_offset;    /* byte offset of the fp32 bias (cout entries) in the blob          */
   sceneego_vol_layout_t lay_src, lay_dst;
@@ -181,11 +183,13 @@ typedef struct sceneego_v2v_op {
 
 /* Host-side fold + repack (replaces nn.BatchNorm3d eval, v2v.py:13,26,29,37,62, at load time).
  *   h_weight: Conv3d (cout,cin,k,k,k) fp32, or ConvTranspose3d (cin,cout,2,2,2) if transposed
- *   bn_*: NULL for no BatchNorm.  Output: bf16 [tap][cin_pad/8][cout_pad][8] and fp32 bias. */
+ *   bn_*: NULL for no BatchNorm.  Output: bf16 [tap][cin_pad/8][cout_pad][8] and fp32 bias.
+ *   xstack > 1: Toeplitz-stacked for x-stacking, [(k+xstack-1)*k*k][cin_pad/8][xstack*cout_pad][8]:
+ *   column block s of input-plane offset dxp holds W[dx = dxp - s] (zero where out of range). */
 int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
                            const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
                            double eps, int cout, int cin, int ksize, int transposed, int cout_pad,
-                           int cin_pad, uint16_t* h_w_out, float* h_b_out);
+                           int cin_pad, int xstack, uint16_t* h_w_out, float* h_b_out);
 
 /* Execute `n_ops` steps on `batch` frames.  d_blob: packed weights + biases. */
 int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,

@@ -120,6 +120,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ---------------------------------------------------------------------------
 // conv parameters
 // ---------------------------------------------------------------------------
+// Division by a runtime constant via a 48-bit reciprocal: exact while n * d < 2^48 (host-checked).
+struct FastDiv { uint64_t m; uint32_t d; };
+static inline FastDiv make_fastdiv(uint32_t d) { FastDiv f; f.d = d; f.m = (1ull << 48) / d + 1; return f; }
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)n * f.m) >> 48); }
+
 struct ConvParams {
   const __nv_bfloat16* src;
   __nv_bfloat16* dst;
@@ -130,6 +135,18 @@ struct ConvParams {
   sceneego_vol_layout_t ls, ld;
   int batch;
   int k, r, cin_planes, ksteps, N, cout_real, flags;
+  // x-stacking (XS > 1): one GEMM row produces the outputs of XS consecutive x-planes, N = xs * n0
+  // columns, against weights Toeplitz-stacked over n_dx = k + xs - 1 input plane offsets.  Work
+  // items are then plane-aligned: (frame, group of xs planes, chunk of L cells inside the plane).
+  int xs, n0, n_dx, n_xg, items_per_plane;
+  FastDiv fd_frame, fd_px, fd_py;   // by ls.frame_pitch, ls.pitch_x, ls.pitch_y
+  // transposed conv k2 s2 on the same kernel: rows = input positions, every output parity is a "tap"
+  // with its own weight block (no row shift) accumulating into its own n0 TMEM columns; the epilogue
+  // scatters column block `par` to output voxel (2x+i, 2y+j, 2z+l).  One launch covers parities
+  // [par0, par0 + taps_dx).
+  int deconv, par0;
+  int taps_dx;                      // taps per window stage: k*k (conv) or parities per launch (deconv)
+  int mma_n;                        // N of one tcgen05.mma: xs*n0 (conv) or n0 (deconv)
   int tiles, L, WL;                 // tiles per item, positions per item, window length (positions)
   int n_items;
   int win_stages, w_slots, wchunk_taps, wchunks_per_dx;
@@ -138,26 +155,29 @@ struct ConvParams {
   uint32_t tmem_cols, half_cols;
 };
 
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_EPI_WARPS = 8;
+constexpr int CONV_THREADS = 64 + 32 * CONV_EPI_WARPS;   // producer warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 4, MAX_WSLOTS = 8;
 
 struct RowInfo {
   bool write;    // position belongs to a frame (valid voxel or in-frame pad)
   bool valid;    // a real voxel
   int b, n;      // frame and flat voxel index (valid only)
+  int x, y, z;   // voxel coordinates in the source volume
   int64_t dpos;  // position in the destination layout
 };
 
-__device__ __forceinline__ RowInfo decode_row(const ConvParams& p, int64_t q) {
+__device__ __forceinline__ RowInfo decode_row(const ConvParams& p, int64_t q64) {
   RowInfo ri;
-  ri.write = false; ri.valid = false; ri.b = 0; ri.n = 0; ri.dpos = 0;
+  ri.write = false; ri.valid = false; ri.b = 0; ri.n = 0; ri.dpos = 0; ri.x = ri.y = ri.z = 0;
   const int S = p.ls.side;
-  const int64_t b = q / p.ls.frame_pitch;
-  const int rem = (int)(q - b * p.ls.frame_pitch) - p.ls.guard;
-  if (b >= p.batch || rem < 0) return ri;
-  const int x = rem / p.ls.pitch_x;
+  const uint32_t q = (uint32_t)q64;                       // batch * frame_pitch < 2^29 (checked on the host)
+  const uint32_t b = fdiv(q, p.fd_frame);
+  const int rem = (int)(q - b * (uint32_t)p.ls.frame_pitch) - p.ls.guard;
+  if ((int)b >= p.batch || rem < 0) return ri;
+  const int x = (int)fdiv((uint32_t)rem, p.fd_px);
   const int r2 = rem - x * p.ls.pitch_x;
-  const int y = r2 / p.ls.pitch_y;
+  const int y = (int)fdiv((uint32_t)r2, p.fd_py);
   const int z = r2 - y * p.ls.pitch_y;
   if (x >= S) return ri;
   // cells of the destination layout reachable from this source cell: voxels and the
@@ -166,8 +186,26 @@ __device__ __forceinline__ RowInfo decode_row(const ConvParams& p, int64_t q) {
   ri.write = true;
   ri.valid = (y < S) && (z < S);
   ri.b = (int)b;
+  ri.x = x; ri.y = y; ri.z = z;
   ri.n = (x * S + y) * S + z;
-  ri.dpos = b * p.ld.frame_pitch + p.ld.guard + (int64_t)x * p.ld.pitch_x + (int64_t)y * p.ld.pitch_y + z;
+  ri.dpos = (int64_t)b * p.ld.frame_pitch + p.ld.guard + (int64_t)x * p.ld.pitch_x + (int64_t)y * p.ld.pitch_y + z;
+  return ri;
+}
+
+// Plane-aligned variant (x-stacked items): `cell` is the index inside x-plane `x` of frame `b`.
+__device__ __forceinline__ RowInfo decode_row_plane(const ConvParams& p, int b, int x, int cell) {
+  RowInfo ri;
+  ri.write = false; ri.valid = false; ri.b = b; ri.n = 0; ri.dpos = 0; ri.x = x; ri.y = ri.z = 0;
+  const int S = p.ls.side;
+  if (cell >= p.ls.pitch_x) return ri;
+  const int y = (int)fdiv((uint32_t)cell, p.fd_py);
+  const int z = cell - y * p.ls.pitch_y;
+  if (y >= S + p.ld.pad || z >= S + p.ld.pad) return ri;
+  ri.write = true;
+  ri.valid = (y < S) && (z < S);
+  ri.y = y; ri.z = z;
+  ri.n = (x * S + y) * S + z;
+  ri.dpos = (int64_t)b * p.ld.frame_pitch + p.ld.guard + (int64_t)x * p.ld.pitch_x + (int64_t)y * p.ld.pitch_y + z;
   return ri;
 }
 
@@ -206,6 +244,12 @@ __device__ __forceinline__ void store_row16_pre(const ConvParams& p, const RowIn
     }
     return;
   }
+  float bs[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+    bs[4 * j] = b4.x; bs[4 * j + 1] = b4.y; bs[4 * j + 2] = b4.z; bs[4 * j + 3] = b4.w;
+  }
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     float o[8];
@@ -215,7 +259,7 @@ __device__ __forceinline__ void store_row16_pre(const ConvParams& p, const RowIn
       unpack8(g ? r1 : r0, rr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float t = v[8 * g + j] + s_bias[c0 + 8 * g + j];
+        float t = v[8 * g + j] + bs[8 * g + j];
         if (p.flags & SCENEEGO_F_RESIDUAL) t += rr[j];
         if (p.flags & SCENEEGO_F_RELU) t = fmaxf(t, 0.f);
         if (p.flags & SCENEEGO_F_ADD_AFTER) t += rr[j];
@@ -253,7 +297,7 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& 
 // descriptors differ by constants: the single issuing lane must sustain one tcgen05.mma per
 // ~41 cycles (measured floor at N<=32, tools/mma_rate.cu).
 // ---------------------------------------------------------------------------
-template <int KSTEPS, int TILES>
+template <int KSTEPS, int TILES, int XS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are
@@ -270,11 +314,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             B_TMEM_FULL = 2 * MAX_STAGES + 2 * MAX_WSLOTS, B_TMEM_EMPTY = B_TMEM_FULL + 2, B_COUNT = B_TMEM_EMPTY + 2;
   uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
-  for (int i = threadIdx.x; i < p.N; i += CONV_THREADS) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n0; i += CONV_THREADS) s_bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), 1); mbar_init(BAR(B_EMPTY_WIN + i), 1); }
     for (int i = 0; i < MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), 1); mbar_init(BAR(B_EMPTY_W + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), 1); mbar_init(BAR(B_TMEM_EMPTY + i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), 1); mbar_init(BAR(B_TMEM_EMPTY + i), CONV_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -291,14 +335,24 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int halo = p.r * (p.ls.pitch_y + 1);   // window starts `halo` positions before the item
   constexpr int L = TILES * 128;
+  // first position of work item `item`; for x-stacked items also frame / first plane / first cell
+  auto item_origin = [&](int item, int& b, int& x0, int& cell0) -> int64_t {
+    if (XS == 1) { b = 0; x0 = 0; cell0 = 0; return (int64_t)p.ls.guard + (int64_t)item * L; }
+    const int c = item % p.items_per_plane;
+    const int t = item / p.items_per_plane;
+    const int xg = t % p.n_xg;
+    b = t / p.n_xg; x0 = xg * XS; cell0 = c * L;
+    return (int64_t)b * p.ls.frame_pitch + p.ls.guard + (int64_t)x0 * p.ls.pitch_x + cell0;
+  };
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
       int ws = 0, wph = 0, sl = 0, sph = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * L;
-        for (int dx = 0; dx < p.k; ++dx) {
+        int ib, ix0, icell0;
+        const int64_t q0 = item_origin(blockIdx.x + it * gridDim.x, ib, ix0, icell0);
+        for (int dx = 0; dx < p.n_dx; ++dx) {
           mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
           mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * (2 * KSTEPS));
           const int64_t qs = q0 + (int64_t)(dx - p.r) * p.ls.pitch_x - halo;
@@ -326,18 +380,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = elect_one();
     // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=p.N
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.mma_n >> 3) << 17) | (8u << 24);
     // K-major no-swizzle: LBO = byte stride between the two 8-channel K chunks of one MMA,
     // SBO = byte stride between 8-row core matrices (validated on B200 hardware).
     // hi word: SBO = 128 B (>>4 = 8) | descriptor version 1 (bit 46 -> bit 14 of the hi word)
     const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
     const uint32_t a_lo_flags = ((p.win_bytes >> 4) & 0x3FFFu) << 16;          // LBO = window plane stride
-    const uint32_t b_lo_flags = (((uint32_t)p.N * 16u >> 4) & 0x3FFFu) << 16;  // LBO = Cout * 16 B
+    const uint32_t b_lo_flags = (((uint32_t)p.mma_n * 16u >> 4) & 0x3FFFu) << 16;  // LBO = N * 16 B
     const uint32_t a_ks_step = (2u * p.win_bytes) >> 4;                        // two planes per K step
-    const uint32_t b_ks_step = (2u * (uint32_t)p.N * 16u) >> 4;
+    const uint32_t b_ks_step = (2u * (uint32_t)p.mma_n * 16u) >> 4;
     const uint32_t b_tap_step = p.tap_bytes >> 4;
     const uint32_t n_cols = (uint32_t)p.N;
     const int pitch_y = p.ls.pitch_y, ksz = p.k, wtaps = p.wchunk_taps;
+    const uint32_t is_deconv = (uint32_t)p.deconv, par_cols = (uint32_t)p.n0;
     int ws = 0, wph = 0, sl = 0, sph = 0;
     for (int it = 0; it < my_items; ++it) {
       const int buf = it & 1;
@@ -345,11 +400,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       tc_fence_after();
       const uint32_t d0 = tmem_u + (uint32_t)buf * p.half_cols;
       uint32_t acc = 0;
-      for (int dx = 0; dx < ksz; ++dx) {
+      for (int dx = 0; dx < p.n_dx; ++dx) {
         mbar_wait_warp(BAR(B_FULL_WIN + ws), wph);
         const uint32_t win_lo = (((sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS) * p.win_bytes) >> 4) & 0x3FFFu) |
                                 a_lo_flags;
         int dy = 0, dz = 0;
+        uint32_t dcol = 0;                                                     // deconv: parity column block
         for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
           mbar_wait_warp(BAR(B_FULL_W + sl), sph);
           tc_fence_after();
@@ -361,13 +417,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
               for (int t = 0; t < TILES; ++t) {
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks)
-                  tc_mma_bf16(d0 + (uint32_t)t * n_cols, desc_hi | (a_lo + (uint32_t)t * 128u + (uint32_t)ks * a_ks_step),
+                  tc_mma_bf16(d0 + (uint32_t)t * n_cols + dcol,
+                              desc_hi | (a_lo + (uint32_t)t * 128u + (uint32_t)ks * a_ks_step),
                               desc_hi | (b_lo + (uint32_t)ks * b_ks_step), idesc, ks == 0 ? acc : 1u);
               }
             }
-            acc = 1;
             b_lo += b_tap_step;
-            if (++dz == ksz) { dz = 0; ++dy; }
+            if (is_deconv) { dcol += par_cols; }                               // next parity: fresh columns, acc stays 0
+            else { acc = 1; if (++dz == ksz) { dz = 0; ++dy; } }
           }
           if (leader) tc_commit(BAR(B_EMPTY_W + sl));
           if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
@@ -382,33 +439,73 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     // ===================== epilogue (warps 2..5) =====================
     // Chunks of 16 output channels; the residual cells of chunk i+1 are requested before chunk i
     // is processed so that their global-load latency overlaps the TMEM read and the math.
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // Eight warps: two per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31).  The pair
+    // splits the item by tile parity (by column-chunk parity when the item is a single tile).
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int nch = p.N >> 4;
+    const int S = p.ls.side;
+    const int t_first = TILES >= 2 ? half : 0, t_step = TILES >= 2 ? 2 : 1;
+    const int c_first = TILES >= 2 ? 0 : half, c_step = TILES >= 2 ? 1 : 2;
+    // x-stacked ops: column chunk c belongs to output plane x0 + (16c / n0), channels (16c % n0)..+15
+    auto shifted = [&](const RowInfo& ri, int x0, int c, int& ch0) -> RowInfo {
+      if (XS == 1 && p.deconv) {
+        const int blk = (c << 4) / p.n0;
+        const int par = p.par0 + blk;
+        ch0 = (c << 4) - blk * p.n0;
+        RowInfo r = ri;
+        r.write = ri.valid;                                  // pads of the 2x volume are never touched
+        r.dpos = (int64_t)ri.b * p.ld.frame_pitch + p.ld.guard + (int64_t)(2 * ri.x + (par >> 2)) * p.ld.pitch_x +
+                 (int64_t)(2 * ri.y + ((par >> 1) & 1)) * p.ld.pitch_y + (2 * ri.z + (par & 1));
+        return r;
+      }
+      if (XS == 1) { ch0 = c << 4; return ri; }
+      const int sft = (c << 4) / p.n0;
+      ch0 = (c << 4) - sft * p.n0;
+      RowInfo r = ri;
+      const bool in = (x0 + sft) < S;
+      r.write = ri.write && in;
+      r.valid = ri.valid && in;
+      r.dpos = ri.dpos + (int64_t)sft * p.ld.pitch_x;
+      r.n = ri.n + sft * S * S;
+      return r;
+    };
     for (int it = 0; it < my_items; ++it) {
       const int buf = it & 1;
-      const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * L;
-      RowInfo ri = decode_row(p, q0 + quarter * 32 + lane);
-      uint4 rn0, rn1;
-      load_res16(p, ri, 0, rn0, rn1);
+      int ib, ix0, icell0;
+      const int64_t q0 = item_origin(blockIdx.x + it * gridDim.x, ib, ix0, icell0);
+      auto row_info = [&](int t) -> RowInfo {
+        const int r = t * 128 + quarter * 32 + lane;
+        return XS == 1 ? decode_row(p, q0 + r) : decode_row_plane(p, ib, ix0, icell0 + r);
+      };
+      RowInfo ri = row_info(t_first);
+      uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
+      if (c_first < nch) {
+        int ch0;
+        const RowInfo rs = shifted(ri, ix0, c_first, ch0);
+        load_res16(p, rs, ch0, rn0, rn1);
+      }
       mbar_wait(BAR(B_TMEM_FULL + buf), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = 0; t < TILES; ++t) {
+      for (int t = t_first; t < TILES; t += t_step) {
         RowInfo ri_next = ri;
-        if (t + 1 < TILES) ri_next = decode_row(p, q0 + (t + 1) * 128 + quarter * 32 + lane);
+        if (t + t_step < TILES) ri_next = row_info(t + t_step);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * p.half_cols +
                                (uint32_t)(t * p.N);
-        for (int c = 0; c < nch; ++c) {
+        for (int c = c_first; c < nch; c += c_step) {
           const uint4 r0 = rn0, r1 = rn1;
-          if (c + 1 < nch) load_res16(p, ri, (c + 1) << 4, rn0, rn1);
-          else if (t + 1 < TILES) load_res16(p, ri_next, 0, rn0, rn1);
+          int ch0, chn;
+          const RowInfo rs = shifted(ri, ix0, c, ch0);
+          if (c + c_step < nch) { const RowInfo rp = shifted(ri, ix0, c + c_step, chn); load_res16(p, rp, chn, rn0, rn1); }
+          else if (t + t_step < TILES) { const RowInfo rp = shifted(ri_next, ix0, c_first, chn); load_res16(p, rp, chn, rn0, rn1); }
           uint32_t raw[16];
           tc_ld16(taddr + (uint32_t)(c << 4), raw);
           tc_wait_ld();
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-          store_row16_pre(p, ri, c << 4, v, s_bias, r0, r1);
+          store_row16_pre(p, rs, ch0, v, s_bias, r0, r1);
         }
         ri = ri_next;
       }
@@ -425,8 +522,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 }
 
 typedef void (*conv_tc_fn)(const ConvParams);
-static conv_tc_fn pick_conv_tc(int ksteps, int tiles) {
-#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T>;
+static conv_tc_fn pick_conv_tc(int ksteps, int tiles, int xs) {
+  if (xs == 4 && ksteps == 3 && tiles == 4) return conv_tc_kernel<3, 4, 4>;
+  if (xs == 4 && ksteps == 3 && tiles == 2) return conv_tc_kernel<3, 4 / 2, 4>;
+  if (xs == 4 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 4>;
+  if (xs == 2 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 2>;
+  if (xs == 2 && ksteps == 2 && tiles == 8) return conv_tc_kernel<2, 8, 2>;
+  if (xs == 2 && ksteps == 1 && tiles == 4) return conv_tc_kernel<1, 4, 2>;
+  if (xs == 2 && ksteps == 4 && tiles == 2) return conv_tc_kernel<4, 2, 2>;
+  if (xs != 1) return nullptr;
+#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T, 1>;
   SE_CASE(1, 8) SE_CASE(2, 8) SE_CASE(3, 4) SE_CASE(3, 8) SE_CASE(2, 4) SE_CASE(4, 4) SE_CASE(4, 2) SE_CASE(8, 2)
   SE_CASE(1, 4) SE_CASE(1, 2) SE_CASE(2, 2) SE_CASE(8, 1) SE_CASE(4, 1) SE_CASE(2, 1) SE_CASE(1, 1) SE_CASE(3, 2) SE_CASE(3, 1)
 #undef SE_CASE
@@ -439,8 +544,8 @@ static conv_tc_fn pick_conv_tc(int ksteps, int tiles) {
 // One thread = one position x 16 output channels.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ ConvParams p, int64_t n_pos) {
-  __shared__ float s_bias[128];
-  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias[i];
+  __shared__ __align__(16) float s_bias[128];
+  for (int i = threadIdx.x; i < p.n0; i += blockDim.x) s_bias[i] = p.bias[i];
   __syncthreads();
   const int64_t q = (int64_t)p.ls.guard + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = blockIdx.y * 16;
@@ -459,7 +564,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
           for (int g = 0; g < p.cin_planes; ++g) {
             float a[8];
             unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8), a);
-            const uint4* wrow = reinterpret_cast<const uint4*>(p.w) + ((size_t)tap * p.cin_planes + g) * p.N + c0;
+            const uint4* wrow = reinterpret_cast<const uint4*>(p.w) + ((size_t)tap * p.cin_planes + g) * p.N + c0;  // p.N = xs*n0
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float wv[8];
@@ -562,45 +667,58 @@ static uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB
 
 // Choose tiles / stages / weight chunking for a conv and fill the kernel parameters.
+// SCENEEGO_TILES / SCENEEGO_STAGES override the choice (tuning only).
+static bool try_plan(ConvParams& p, int tiles, int want_stages) {
+  const int taps_dx = p.taps_dx;
+  const int L = tiles * 128;
+  const int WL = L + 2 * p.r * (p.ls.pitch_y + 1);
+  const uint32_t win_bytes = (uint32_t)WL * 16u;
+  const uint32_t stage = win_bytes * p.cin_planes;
+  // weight chunk: as many taps of one dx as fit ~24 KB, must divide k*k
+  int wct = taps_dx;
+  while (wct > 1 && (uint32_t)wct * p.tap_bytes > 24576u) {
+    int nx = wct - 1;
+    while (nx > 1 && taps_dx % nx) --nx;
+    wct = nx;
+  }
+  const uint32_t wchunk = (uint32_t)wct * p.tap_bytes;
+  const uint32_t fixed = 1024;  // bias + barriers + tmem ptr
+  if ((uint64_t)stage * want_stages + fixed + 2ull * wchunk > kMaxSmem) return false;
+  const uint32_t used = stage * want_stages + fixed;
+  int slots = (int)((kMaxSmem - used) / wchunk);
+  if (slots > MAX_WSLOTS) slots = MAX_WSLOTS;
+  if (slots > 4 && wchunk > 8192) slots = 4;
+  p.tiles = tiles; p.L = L; p.WL = WL;
+  p.win_bytes = win_bytes; p.win_stages = want_stages;
+  p.wchunk_taps = wct; p.wchunks_per_dx = taps_dx / wct; p.wchunk_bytes = wchunk; p.w_slots = slots;
+  p.off_win = 0;
+  p.off_w = stage * want_stages;
+  p.off_bias = p.off_w + wchunk * slots;
+  p.off_bar = p.off_bias + 512;
+  p.half_cols = (uint32_t)(tiles * p.N);
+  uint32_t cols = 32;
+  while (cols < 2 * p.half_cols) cols <<= 1;
+  p.tmem_cols = cols;
+  return true;
+}
+
 static int plan_conv(ConvParams& p) {
-  const int taps_dx = p.k * p.k;
-  p.tap_bytes = (uint32_t)p.cin_planes * p.N * 16u;
+  p.tap_bytes = (uint32_t)p.cin_planes * p.mma_n * 16u;   // mma_n includes the x-stacking factor
   int max_tiles = 256 / p.N;
   if (max_tiles > 8) max_tiles = 8;
-  for (int tiles = max_tiles; tiles >= 1; tiles >>= 1) {
-    const int L = tiles * 128;
-    const int WL = L + 2 * p.r * (p.ls.pitch_y + 1);
-    const uint32_t win_bytes = (uint32_t)WL * 16u;
-    const uint32_t stage = win_bytes * p.cin_planes;
-    // weight chunk: as many taps of one dx as fit ~24 KB, must divide k*k
-    int wct = taps_dx;
-    while (wct > 1 && (uint32_t)wct * p.tap_bytes > 24576u) {
-      int nx = wct - 1;
-      while (nx > 1 && taps_dx % nx) --nx;
-      wct = nx;
-    }
-    const uint32_t wchunk = (uint32_t)wct * p.tap_bytes;
-    for (int stages = (p.k == 1 ? 3 : 2); stages >= 2; --stages) {
-      const uint32_t fixed = 1024;  // bias + barriers + tmem ptr
-      const uint32_t used = stage * stages + fixed;
-      if (used + 2 * wchunk > kMaxSmem) continue;
-      int slots = (int)((kMaxSmem - used) / wchunk);
-      if (slots > MAX_WSLOTS) slots = MAX_WSLOTS;
-      if (slots > 4 && wchunk > 8192) slots = 4;
-      p.tiles = tiles; p.L = L; p.WL = WL;
-      p.win_bytes = win_bytes; p.win_stages = stages;
-      p.wchunk_taps = wct; p.wchunks_per_dx = taps_dx / wct; p.wchunk_bytes = wchunk; p.w_slots = slots;
-      p.off_win = 0;
-      p.off_w = stage * stages;
-      p.off_bias = p.off_w + wchunk * slots;
-      p.off_bar = p.off_bias + 512;
-      p.half_cols = (uint32_t)(tiles * p.N);
-      uint32_t cols = 32;
-      while (cols < 2 * p.half_cols) cols <<= 1;
-      p.tmem_cols = cols;
+  const char* et = getenv("SCENEEGO_TILES");
+  const char* es = getenv("SCENEEGO_STAGES");
+  if (et || es) {
+    const int tiles = et ? atoi(et) : max_tiles;
+    const int stages = es ? atoi(es) : 2;
+    if (tiles >= 1 && tiles <= max_tiles && stages >= 1 && stages <= MAX_STAGES && try_plan(p, tiles, stages))
       return (int)(p.off_bar + 512);
-    }
   }
+  // measured on B200 (tools/tune_conv.py): the largest item with a 2-stage window ring wins for every
+  // 3^3 / 7^3 layer; 1x1 convs have no halo, so their small windows get a deeper ring
+  for (int tiles = max_tiles; tiles >= 1; tiles >>= 1)
+    for (int stages = (p.k == 1 ? 4 : 2); stages >= 2; --stages)
+      if (try_plan(p, tiles, stages)) return (int)(p.off_bar + 512);
   return -1;
 }
 
@@ -615,11 +733,15 @@ extern "C" int sceneego_v2v_last_launch_count(void) { return g_launches; }
 extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const float* h_gamma,
                                       const float* h_beta, const float* h_mean, const float* h_var, double eps,
                                       int cout, int cin, int ksize, int transposed, int cout_pad, int cin_pad,
-                                      uint16_t* h_w_out, float* h_b_out) {
+                                      int xstack, uint16_t* h_w_out, float* h_b_out) {
   SE_REQUIRE(h_weight && h_w_out && h_b_out, "pack_conv: null argument");
   SE_REQUIRE(cout_pad >= cout && cin_pad >= cin && cout_pad % 8 == 0 && cin_pad % 8 == 0, "pack_conv: bad padding");
+  SE_REQUIRE(xstack >= 1 && (xstack == 1 || !transposed), "pack_conv: bad xstack");
   const int taps = ksize * ksize * ksize;
-  memset(h_w_out, 0, (size_t)taps * cin_pad * cout_pad * sizeof(uint16_t));
+  const int kk = ksize * ksize;
+  const int n_stk = xstack * cout_pad;                 // columns of the stacked B operand
+  const int n_dx = ksize + xstack - 1;                 // input plane offsets
+  memset(h_w_out, 0, (size_t)n_dx * kk * cin_pad * n_stk * sizeof(uint16_t));
   for (int co = 0; co < cout_pad; ++co) {
     double scale = 1.0, shift = 0.0;
     if (co < cout) {
@@ -636,11 +758,54 @@ extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias
       for (int t = 0; t < taps; ++t) {
         // Conv3d (cout,cin,kx,ky,kz); ConvTranspose3d (cin,cout,kx,ky,kz): tap = output parity
         const size_t src = transposed ? (((size_t)ci * cout + co) * taps + t) : (((size_t)co * cin + ci) * taps + t);
-        const float wv = (float)((double)h_weight[src] * scale);
-        const size_t dst = (((size_t)t * (cin_pad / 8) + ci / 8) * cout_pad + co) * 8 + (ci & 7);
-        h_w_out[dst] = f2bf(wv);
+        const uint16_t wv = f2bf((float)((double)h_weight[src] * scale));
+        // tap t = (dx, dy, dz); output-plane shift s reads input plane offset dxp = dx + s
+        const int dx = t / kk, rest = t % kk;
+        for (int sft = 0; sft < xstack; ++sft) {
+          const size_t tp = (size_t)(dx + sft) * kk + rest;
+          const size_t dst = ((tp * (cin_pad / 8) + ci / 8) * n_stk + (size_t)sft * cout_pad + co) * 8 + (ci & 7);
+          h_w_out[dst] = wv;
+        }
       }
   }
+  return SCENEEGO_OK;
+}
+
+static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t st) {
+  const int64_t n_pos = (int64_t)batch * p.ls.frame_pitch;
+  // fdiv() is exact while n * d < 2^48 and n fits 32 bits
+  SE_REQUIRE(n_pos + 4096 < (1ll << 31) && (n_pos + 4096) * (int64_t)p.ls.frame_pitch < (1ll << 48),
+             "v2v_run: op %d: batch * frame_pitch too large for one launch (use a smaller chunk)", op_index);
+  p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);
+  p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
+  p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
+  const int smem = plan_conv(p);
+  SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", op_index);
+  if (p.xs == 1) {
+    p.n_items = (int)((n_pos + p.L - 1) / p.L);
+  } else {
+    p.items_per_plane = (p.ls.pitch_x + p.L - 1) / p.L;
+    p.n_xg = (p.ls.side + p.xs - 1) / p.xs;
+    p.n_items = batch * p.n_xg * p.items_per_plane;
+  }
+  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  conv_tc_fn fn = pick_conv_tc(p.ksteps, p.tiles, p.xs);
+  SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d xs=%d", op_index, p.ksteps,
+             p.tiles, p.xs);
+  {
+    static conv_tc_fn configured[32];
+    static int n_configured = 0;
+    bool done = false;
+    for (int c = 0; c < n_configured; ++c) done |= (configured[c] == fn);
+    if (!done) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+      if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+      if (n_configured < 32) configured[n_configured++] = fn;
+    }
+  }
+  fn<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
+  SE_CUDA_LAUNCH_CHECK("conv_tc");
+  ++g_launches;
   return SCENEEGO_OK;
 }
 
@@ -674,13 +839,29 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
     p.w = (const __nv_bfloat16*)((const char*)d_blob + op.w_offset);
     p.bias = (const float*)((const char*)d_blob + op.b_offset);
     p.cin_planes = op.cin / 8; p.ksteps = op.cin / 16; p.N = op.cout; p.cout_real = op.cout_real;
+    p.xs = 1; p.n0 = op.cout; p.n_dx = op.ksize; p.n_xg = 0; p.items_per_plane = 0;
     if (op.type == SCENEEGO_OP_DECONV2) {
       SE_REQUIRE(op.lay_dst.side == 2 * op.lay_src.side && op.cin % 8 == 0 && op.cout % 8 == 0, "v2v_run: op %d bad deconv shape", i);
-      const int So = op.lay_dst.side;
-      dim3 grid((So * So * So + 127) / 128, op.cout / 8, batch);
-      deconv2_kernel<<<grid, 128, 0, st>>>(p);
-      SE_CUDA_LAUNCH_CHECK("deconv2");
-      ++g_launches;
+      if (op.impl == 1 || force_simt || op.cin % 16 || op.cout % 16 || op.cout > 256) {
+        const int So = op.lay_dst.side;
+        dim3 grid((So * So * So + 127) / 128, op.cout / 8, batch);
+        deconv2_kernel<<<grid, 128, 0, st>>>(p);
+        SE_CUDA_LAUNCH_CHECK("deconv2");
+        ++g_launches;
+        continue;
+      }
+      // tensor path: 8 parities as taps, 256 / cout parities (TMEM columns) per launch
+      int npar = 256 / op.cout;
+      if (npar > 8) npar = 8;
+      const __nv_bfloat16* w_all = p.w;
+      for (int par0 = 0; par0 < 8; par0 += npar) {
+        ConvParams q = p;
+        q.k = 1; q.r = 0; q.xs = 1; q.n0 = op.cout; q.mma_n = op.cout; q.N = npar * op.cout; q.n_dx = 1;
+        q.deconv = 1; q.par0 = par0; q.taps_dx = npar;
+        q.w = w_all + (size_t)par0 * q.cin_planes * op.cout * 8;
+        const int rc = launch_conv_tc(q, batch, i, st);
+        if (rc != SCENEEGO_OK) return rc;
+      }
       continue;
     }
     SE_REQUIRE(op.type == SCENEEGO_OP_CONV, "v2v_run: op %d unknown type", i);
@@ -690,33 +871,23 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
                "v2v_run: op %d layouts incompatible with the stencil", i);
     p.k = op.ksize; p.r = op.ksize / 2;
     const int64_t n_pos = (int64_t)batch * p.ls.frame_pitch;
+    p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);      // the checker kernel decodes rows too
+    p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
+    p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
     if (op.impl == 1 || force_simt) {
+      p.n0 = op.cout; p.N = (op.xstack > 1 ? op.xstack : 1) * op.cout;   // weight row stride of the stacked blob
       dim3 grid((unsigned)((n_pos + 127) / 128), op.cout / 16);
       conv_simt_kernel<<<grid, 128, 0, st>>>(p, n_pos);
       SE_CUDA_LAUNCH_CHECK("conv_simt");
       ++g_launches;
       continue;
     }
-    const int smem = plan_conv(p);
-    SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", i);
-    p.n_items = (int)((n_pos + p.L - 1) / p.L);
-    const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-    conv_tc_fn fn = pick_conv_tc(p.ksteps, p.tiles);
-    SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d", i, p.ksteps, p.tiles);
-    {
-      static conv_tc_fn configured[32];
-      static int n_configured = 0;
-      bool done = false;
-      for (int c = 0; c < n_configured; ++c) done |= (configured[c] == fn);
-      if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-        if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-        if (n_configured < 32) configured[n_configured++] = fn;
-      }
-    }
-    fn<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
-    SE_CUDA_LAUNCH_CHECK("conv_tc");
-    ++g_launches;
+    const int xs = op.xstack > 1 ? op.xstack : 1;
+    SE_REQUIRE(xs * op.cout <= 256, "v2v_run: op %d: xstack * cout exceeds 256 columns", i);
+    p.xs = xs; p.n0 = op.cout; p.N = xs * op.cout; p.mma_n = p.N; p.n_dx = op.ksize + xs - 1;
+    p.deconv = 0; p.par0 = 0; p.taps_dx = op.ksize * op.ksize;
+    const int rc = launch_conv_tc(p, batch, i, st);
+    if (rc != SCENEEGO_OK) return rc;
   }
   if (ev) cudaEventRecord(ev[n_ops], st);
   return SCENEEGO_OK;

@@ -140,14 +140,15 @@ class _Program:
         self.blob_bytes += raw.size
         return off
 
-    def pack(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int) -> Tuple[int, int]:
+    def pack(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
+             xstack: int = 1) -> Tuple[int, int]:
         transposed = isinstance(conv, nn.ConvTranspose3d)
         w = conv.weight.detach().float().cpu().contiguous().numpy()
         k = w.shape[-1]
         cin, cout = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
         bias = conv.bias.detach().float().cpu().contiguous().numpy() if conv.bias is not None else None
-        taps = k ** 3
-        w_out = np.zeros(taps * cin_pad * cout_pad, dtype=np.uint16)
+        taps = (k + xstack - 1) * k * k
+        w_out = np.zeros(taps * cin_pad * cout_pad * xstack, dtype=np.uint16)
         b_out = np.zeros(cout_pad, dtype=np.float32)
 
         def fp(a):
@@ -163,20 +164,21 @@ class _Program:
             eps = 0.0
         rc = _lib.load_library().sceneego_v2v_pack_conv(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var),
                                                         C.c_double(eps), cout, cin, k, int(transposed), cout_pad,
-                                                        cin_pad, fp(w_out), fp(b_out))
+                                                        cin_pad, int(xstack), fp(w_out), fp(b_out))
         _lib._check(rc, "v2v_pack_conv")
         return self._append_blob(w_out), self._append_blob(b_out)
 
     # -- ops -----------------------------------------------------------------
-    def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False):
+    def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False,
+             xstack: int = 1):
         k = conv.kernel_size[0]
         cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
-        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad)
+        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad, xstack)
         op = _lib.V2VOp()
         op.type = _lib.OP_CONV
         op.flags = (_lib.F_RELU if relu else 0) | (_lib.F_RESIDUAL if res >= 0 else 0) | (_lib.F_OUT_F32 if out_f32 else 0)
         op.ksize, op.cin, op.cout, op.cout_real = k, cin_pad, cout_pad, conv.out_channels
-        op.src, op.dst, op.res, op.impl = src, dst, res, 0
+        op.src, op.dst, op.res, op.impl, op.xstack = src, dst, res, 0, xstack
         op.w_offset, op.b_offset = w_off, b_off
         op.lay_src = self.lay_of(src)
         op.lay_dst = self.lay_of(dst) if not out_f32 else self.lay_of(src)
@@ -226,6 +228,8 @@ class V2VModel(nn.Module):
         super().__init__()
         self.input_channels, self.output_channels = input_channels, output_channels
         self.max_chunk = max_chunk
+        self.stem_xstack = 4
+        self.c32_xstack = 2      # 3^3 convs with Cout = 32: stack two x-planes (N = 64)
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
                                           Res3DBlock(32, 32), Res3DBlock(32, 32))
         self.encoder_decoder = EncoderDecorder()
@@ -252,15 +256,16 @@ class V2VModel(nn.Module):
         self._programs.clear()
 
     def _res(self, pg: _Program, blk: Res3DBlock, x: int, level: int) -> int:
+        xs = self.c32_xstack if blk.res_branch[0].out_channels == 32 else 1
         t = pg.acquire(level)
-        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True)
+        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs)
         if len(blk.skip_con) > 0:
             s = pg.acquire(level)
             pg.conv(blk.skip_con[0], blk.skip_con[1], x, s, relu=False)
         else:
             s = x
         y = pg.acquire(level)
-        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s)
+        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s, xstack=xs)
         pg.release(t)
         if s != x:
             pg.release(s)
@@ -272,7 +277,10 @@ class V2VModel(nn.Module):
         pg = _Program(side, chunk, self.input_channels, device)
         ed = self.encoder_decoder
         x = pg.acquire(0)
-        pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True)
+        # 7^3 stem, Cout = 16: the worst tcgen05 shape (N = 16 costs as much as N = 32 per MMA), so four
+        # adjacent x-planes of outputs are stacked into N = 64 (tools/mma_rate.cu for the cost model)
+        pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True,
+                xstack=self.stem_xstack)
         for i in (1, 2, 3):
             y = self._res(pg, self.front_layers[i], x, 0)
             pg.release(x)

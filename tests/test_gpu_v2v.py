@@ -87,6 +87,30 @@ def test_single_conv(cin, cout, k, S, B, pad_src, impl):
     assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
 
 
+@pytest.mark.parametrize("cin,cout,k,S,B,pad_src,xs", [(33, 16, 7, 16, 2, 3, 4), (33, 16, 7, 64, 1, 3, 4),
+                                                        (32, 32, 3, 16, 3, 1, 2), (32, 16, 3, 8, 2, 1, 4)])
+def test_x_stacked_conv(cin, cout, k, S, B, pad_src, xs):
+    """x-stacking: GEMM rows produce `xs` consecutive x-planes against Toeplitz-stacked weights."""
+    conv, bn = _mk_conv(cin, cout, k, seed=99 + xs)
+    g = torch.Generator().manual_seed(S * 7 + B)
+    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    res = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
+    got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, pad_src=pad_src, xstack=xs)
+    _close(got, _ref(x, conv, bn, True, res=res), f"xstack{xs} conv {cin}->{cout} k{k} S{S}")
+    plain, _, _ = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, pad_src=pad_src, xstack=1)
+    assert ((got - plain).abs() <= 0.0079 * plain.abs() + 1e-4).all()      # same math, other summation order
+    ref_simt, _, _ = util.run_single_op(x, conv, bn, relu=True, res=res, impl=1, pad_src=pad_src, xstack=xs)
+    assert ((got - ref_simt).abs() <= 0.0079 * ref_simt.abs() + 1e-4).all()  # checker reads the stacked blob
+    plane = dst[0].float()
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(S, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
+
+
 @pytest.mark.parametrize("cin,cout,S,B", [(32, 32, 16, 2), (128, 128, 4, 2), (16, 32, 32, 1)])
 def test_tc_matches_simt_bitwise_close(cin, cout, S, B):
     """Same packed weights, same bf16 inputs: tensor-core and CUDA-core paths may differ only

@@ -69,7 +69,7 @@ def test_pack_conv_folds_batchnorm():
         bp = np.zeros(cout_p, np.float32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         assert lib.sceneego_v2v_pack_conv(p(w), p(b), p(gamma), p(beta), p(mean), p(var), C.c_double(1e-5), cout, cin,
-                                          k, tr, cout_p, cin_p, p(wp), p(bp)) == 0
+                                          k, tr, cout_p, cin_p, 1, p(wp), p(bp)) == 0
         scale = gamma.astype(np.float64) / np.sqrt(var.astype(np.float64) + 1e-5)
         wf = (w.transpose(1, 0, 2, 3, 4) if tr else w).reshape(cout, cin, taps) * scale[:, None, None]
         got = _unpack(wp, taps, cin_p, cout_p)
@@ -82,7 +82,7 @@ def test_pack_conv_folds_batchnorm():
     w = rng.standard_normal((15, 32, 1, 1, 1)).astype(np.float32)
     wp, bp = np.zeros(32 * 16, np.uint16), np.zeros(16, np.float32)
     assert lib.sceneego_v2v_pack_conv(w.ctypes.data_as(C.c_void_p), None, None, None, None, None, C.c_double(0), 15, 32,
-                                      1, 0, 16, 32, wp.ctypes.data_as(C.c_void_p), bp.ctypes.data_as(C.c_void_p)) == 0
+                                      1, 0, 16, 32, 1, wp.ctypes.data_as(C.c_void_p), bp.ctypes.data_as(C.c_void_p)) == 0
     assert np.all(bp == 0)
 
 

@@ -11,6 +11,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 CALIB = os.path.join(ROOT, "sceneego_b200", "data", "fisheye.calibration_05_08.json")
 
 
+LAST_PROGRAM = None
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name))
 
@@ -36,7 +39,7 @@ def unpack_bits(packed, V):
     return np.unpackbits(packed)[: V ** 3].reshape(V, V, V).astype(np.float32)
 
 
-def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None):
+def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None, xstack=1):
     """Run one V2V op (conv or deconv) through sceneego_v2v_run; x (B,Cin,S,S,S) f32 cuda."""
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program, _pad16
@@ -69,9 +72,11 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     if deconv:
         pg.deconv(conv, bn, 0, 1, add=r_idx)
     else:
-        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx)
+        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack)
     pg.ops[0].impl = impl
     pg.finalize()
+    global LAST_PROGRAM
+    LAST_PROGRAM = pg
     lib = _lib.load_library()
     rc = lib.sceneego_v2v_run(pg.op_array, 1, pg.buf_ptrs, C.c_void_p(pg.blob.data_ptr()), B, _lib._stream())
     _lib._check(rc, "v2v_run")
