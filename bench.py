@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=64, help="frames per V2V launch group")
     ap.add_argument("--profile-ops", default="", help="write the per-op V2V timing table to this file")
     return ap.parse_args()
 
@@ -47,6 +48,7 @@ def workload_config(frames, world):
             "parallelism": f"frame-shard x{world}, NCCL all-gather of poses",
             "weights": "random init (seeded), BatchNorm statistics randomised",
             "outputs": "reference-identical 4-tuple (features and softmaxed volumes materialised)",
+            "v2v_chunk_frames": None,
             "l2_policy": "inputs (604 MB/step) and activations (>1 GB/layer) exceed the 126 MB L2"}
 
 
@@ -165,7 +167,7 @@ def ours_arm(args):
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        net = VoxelNetwork_depth(util.load_config(batch_size=B), device=f"cuda:{local}").eval()
+        net = VoxelNetwork_depth(util.load_config(batch_size=B), device=f"cuda:{local}", v2v_chunk=args.chunk).eval()
     sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn")
     full = net.state_dict()
     full.update(sd)
@@ -250,10 +252,12 @@ def ours_arm(args):
                 "traffic": None, "peak_source": peak_src,
                 "how": "algorithmic 2*Cin*Cout*k^3*V^3 FLOPs of the conv ops / sum of their CUDA-event durations "
                        "(sceneego_v2v_run_profile), per frame"}
+        cfg = workload_config(B, world)
+        cfg["v2v_chunk_frames"] = min(args.chunk, B)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(B, world), "clocks": clocks,
+                "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes // args.steps,
                         "d2h_bytes_per_step": pipe.d2h_bytes // args.steps,
                         "api": "sceneego_b200.pipeline.HostStagePipeline.run (pinned host -> poses on host)"},
@@ -331,6 +335,12 @@ def stage_kernel_timings(net, feat_d, depth_d, B, args):
         json.dump(table, open(args.profile_ops, "w"), indent=1)
     ms = timed(lambda: _lib.softargmax3d(logits, 1.0, True, net._axis, None, False))
     rec("softargmax", ms, J * V ** 3 * 4, "read (15,64,64,64) f32 logits once (online softmax)")
+    ms_full = timed(lambda: _lib.softargmax3d(logits, 1.0, True, net._axis, None, True))
+    rec("softmax_volume_write", max(ms_full - ms, 1e-6), 2 * J * V ** 3 * 4,
+        "output #3 of the reference forward: read logits again + write (15,64,64,64) f32")
+    ms = timed(lambda: _lib.features_upsample_pad(feat32, 1024, 128))
+    rec("features_upsample_pad", ms, 32 * 1024 * 1280 * 4 + 64 * 64 * 32 * 4,
+        "output #2 of the reference forward: write (32,1024,1280) f32")
     return out
 
 

@@ -1,6 +1,7 @@
 // Camera tables, depth-map voxelisation (a4/a5) and fused unprojection (a1-a3, a6).
 // All kernels here are HBM-bound byte/float work: coalesced, vectorised, no tensor cores.
 #include "common.cuh"
+#include <math.h>
 
 namespace sceneego {
 
@@ -181,22 +182,28 @@ __global__ void __launch_bounds__(256) feature_conv1x1_kernel(const float* __res
 }
 
 // Output #2 of the reference forward: nearest upsample + pad, materialised only on request.
-__global__ void upsample_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int c, int h, int w,
-                                    int up, int pad) {
+// Pure write bandwidth (168 MB per frame).  One CTA = one (frame, channel, source row): the
+// up/h identical output rows are built once in registers (one float4 per thread) and stored
+// up/h times with streaming stores.
+__global__ void __launch_bounds__(320) upsample_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int c,
+                                                          int h, int w, int up, int pad) {
   const int W = up + 2 * pad;
-  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y;
-  const int bc = blockIdx.z;
-  if (x4 >= W) return;
+  const int sy = blockIdx.x;
+  const int bc = blockIdx.y;
   const int b = bc / c, ch = bc % c;
-  const int sy = (int)(((long long)y * h) / up);
-  float v[4];
+  const int rows = up / h;                       // output rows fed by one source row
+  const float* src = in + (((size_t)b * h + sy) * w) * c + ch;
+  for (int x4 = threadIdx.x * 4; x4 < W; x4 += blockDim.x * 4) {
+    float v[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = x4 + i - pad;
-    v[i] = (x >= 0 && x < up) ? in[(((size_t)b * h + sy) * w + (int)(((long long)x * w) / up)) * c + ch] : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int x = x4 + i - pad;
+      v[i] = (x >= 0 && x < up) ? __ldg(src + (size_t)(int)(((long long)x * w) / up) * c) : 0.f;
+    }
+    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    float* dst = out + ((size_t)bc * up + (size_t)sy * rows) * W + x4;
+    for (int r = 0; r < rows; ++r) __stcs(reinterpret_cast<float4*>(dst + (size_t)r * W), o);
   }
-  *reinterpret_cast<float4*>(out + ((size_t)bc * up + y) * W + x4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // ---------------------------------------------------------------------------
@@ -290,19 +297,20 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
 // row-major, so depth, ray table (24 B / pixel, L2 resident across frames) and the
 // zero-padding test are all coalesced.  The scatter is a benign same-value race.
 // ---------------------------------------------------------------------------
+template <bool kPow2Side>
 __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__ depth, int h, int w,
                                                       const double* __restrict__ ray, int img_h, int img_w, int V,
-                                                      double side, float* __restrict__ occ_f32,
+                                                      double side, double inv_side, float* __restrict__ occ_f32,
                                                       __nv_bfloat16* __restrict__ occ_bf16,
                                                       sceneego_vol_layout_t lay, int channel) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y;
   const int b = blockIdx.z;
-  if (X >= img_w) return;
   const int pad = (img_w - img_h) / 2;
   const int xs = X - pad;
   float dv = 0.f;
-  if (xs >= 0 && xs < img_h) {
+  const bool in_img = X < img_w;
+  if (in_img && xs >= 0 && xs < img_h) {
     // cv2.resize(INTER_NEAREST): src = min(floor(dst * in / out), in - 1)
     int sy = (int)(((long long)Y * h) / img_h);
     int sx = (int)(((long long)xs * w) / img_h);
@@ -310,16 +318,47 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
     sx = sx < w - 1 ? sx : w - 1;
     dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
   }
-  const double d = (double)dv;
-  const double* r = ray + ((size_t)Y * img_w + X) * 3;
-  const double half = side / 2;             // cuboid_side / 2
-  const double Vd = (double)V;
-  const double qx = rint(__ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(r[0], d), half), Vd), side));
-  const double qy = rint(__ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(r[1], d), half), Vd), side));
-  const double qz = rint(__ddiv_rn(__dmul_rn(__dmul_rn(r[2], d), Vd), side));
-  const double hi = (double)(V - 1);
-  if (qx >= 0.0 && qx <= hi && qy >= 0.0 && qy <= hi && qz >= 0.0 && qz <= hi) {
-    const int ix = (int)qx, iy = (int)qy, iz = (int)qz;
+  int ix = -1, iy = 0, iz = 0;
+  const bool zero = in_img && (dv == 0.0f);
+  if (in_img && !zero) {
+    const double d = (double)dv;
+    const double* r = ray + ((size_t)Y * img_w + X) * 3;
+    const double half = side / 2;             // cuboid_side / 2
+    const double Vd = (double)V;
+    double qx = __dmul_rn(__dadd_rn(__dmul_rn(r[0], d), half), Vd);
+    double qy = __dmul_rn(__dadd_rn(__dmul_rn(r[1], d), half), Vd);
+    double qz = __dmul_rn(__dmul_rn(r[2], d), Vd);
+    if (kPow2Side) {   // x / 2^k == x * 2^-k exactly (no fp64 divide on the hot path)
+      qx = __dmul_rn(qx, inv_side); qy = __dmul_rn(qy, inv_side); qz = __dmul_rn(qz, inv_side);
+    } else {
+      qx = __ddiv_rn(qx, side); qy = __ddiv_rn(qy, side); qz = __ddiv_rn(qz, side);
+    }
+    qx = rint(qx); qy = rint(qy); qz = rint(qz);
+    const double hi = (double)(V - 1);
+    if (qx >= 0.0 && qx <= hi && qy >= 0.0 && qy <= hi && qz >= 0.0 && qz <= hi) {
+      ix = (int)qx; iy = (int)qy; iz = (int)qz;
+    }
+  }
+  // every zero-depth pixel (all the padded columns, everything outside the image circle) lands on
+  // ray*0 -> q = (rint((0+s/2)*V/s), same, 0): one thread per block writes that voxel
+  const int any_zero = __syncthreads_or(zero ? 1 : 0);
+  if (any_zero && threadIdx.x == 0 && ix < 0) {
+    const double half = side / 2, Vd = (double)V;
+    const double q0 = rint(kPow2Side ? __dmul_rn(__dmul_rn(half, Vd), inv_side) : __ddiv_rn(__dmul_rn(half, Vd), side));
+    if (q0 >= 0.0 && q0 <= (double)(V - 1)) { ix = (int)q0; iy = (int)q0; iz = 0; }
+  } else if (any_zero && threadIdx.x == 0) {
+    // thread 0 has its own voxel to write: hand the zero-depth voxel to the write below via a second store
+    const double half = side / 2, Vd = (double)V;
+    const double q0 = rint(kPow2Side ? __dmul_rn(__dmul_rn(half, Vd), inv_side) : __ddiv_rn(__dmul_rn(half, Vd), side));
+    if (q0 >= 0.0 && q0 <= (double)(V - 1)) {
+      const int c = (int)q0;
+      if (occ_f32) occ_f32[(((size_t)b * V + c) * V + c) * V] = 1.0f;
+      if (occ_bf16)
+        occ_bf16[((int64_t)(channel >> 3) * lay.plane_stride + vol_pos(lay, b, c, c, 0)) * 8 + (channel & 7)] =
+            __float2bfloat16(1.0f);
+    }
+  }
+  if (ix >= 0) {
     if (occ_f32) occ_f32[(((size_t)b * V + ix) * V + iy) * V + iz] = 1.0f;
     if (occ_bf16) {
       const int64_t pos = vol_pos(lay, b, ix, iy, iz);
@@ -417,8 +456,9 @@ extern "C" int sceneego_features_upsample_pad_f32(const float* d_in, float* d_ou
   SE_REQUIRE(d_in && d_out && batch > 0, "features_upsample_pad: null argument");
   SE_REQUIRE((up + 2 * pad) % 4 == 0, "features_upsample_pad: output width must be a multiple of 4");
   SE_REQUIRE((long long)batch * c <= 65535, "features_upsample_pad: batch*c too large for one launch");
-  dim3 grid(((up + 2 * pad) / 4 + 127) / 128, up, batch * c);
-  upsample_pad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_in, d_out, c, h, w, up, pad);
+  SE_REQUIRE(up % h == 0, "features_upsample_pad: up must be a multiple of h (src = dst * h / up)");
+  dim3 grid(h, batch * c);
+  upsample_pad_kernel<<<grid, 320, 0, (cudaStream_t)stream>>>(d_in, d_out, c, h, w, up, pad);
   SE_CUDA_LAUNCH_CHECK("features_upsample_pad");
   return SCENEEGO_OK;
 }
@@ -458,8 +498,14 @@ extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int 
   SE_REQUIRE(!d_occ_bf16 || (lay && lay->side == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
   dim3 grid((img_w + 255) / 256, img_h, batch);
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
-  voxelize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, d_occ_f32,
-                                                          (__nv_bfloat16*)d_occ_bf16, L, channel);
+  int e2 = 0;
+  const bool pow2 = side > 0 && frexp(side, &e2) == 0.5;       // side == 2^(e2-1): divide == exact multiply
+  if (pow2)
+    voxelize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, 1.0 / side,
+                                                                  d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel);
+  else
+    voxelize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, 0.0,
+                                                                   d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel);
   SE_CUDA_LAUNCH_CHECK("voxelize");
   return SCENEEGO_OK;
 }

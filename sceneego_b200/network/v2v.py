@@ -224,7 +224,7 @@ class V2VModel(nn.Module):
     returns (B,out,V,V,V) f32 logits; the fused path used by VoxelNetwork_depth writes the
     stem input directly (see `input_buffer`) and calls `run_chunk`."""
 
-    def __init__(self, input_channels, output_channels, max_chunk: int = 16):
+    def __init__(self, input_channels, output_channels, max_chunk: int = 32):
         super().__init__()
         self.input_channels, self.output_channels = input_channels, output_channels
         self.max_chunk = max_chunk

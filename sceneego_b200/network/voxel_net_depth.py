@@ -41,7 +41,7 @@ def _resolve_calibration(path):
 
 class VoxelNetwork_depth(nn.Module):
     def __init__(self, config, device='cuda', materialize_features=True, materialize_volumes=True,
-                 fused_projection=False, v2v_chunk=16):
+                 fused_projection=False, v2v_chunk=32):
         """Extra keyword switches (all default to reference-identical outputs):
         materialize_features / materialize_volumes: build outputs #2 / #3 of the reference
             forward (168 MB and 15.7 MB per frame, ignored by demo.py:57 / test.py:54);

@@ -17,10 +17,14 @@ def get_projected_2d_points_with_coord_volumes(fisheye_model, coord_volume):
 
 def get_grid_coord_proj_batch(grid_coord_proj, batch_size, heatmap_shape):
     """utils/op.py:177-184 -- normalise to [-1,1], shape (B,N,1,2), batch dim stride 0.
-    Elementwise table preparation done once at construction (torch, any device)."""
-    g = torch.zeros_like(grid_coord_proj)
-    g[:, 0] = 2 * (grid_coord_proj[:, 0] / heatmap_shape[1] - 0.5)
-    g[:, 1] = 2 * (grid_coord_proj[:, 1] / heatmap_shape[0] - 0.5)
+    Table preparation done once at construction.  The arithmetic runs on the host: torch's CUDA
+    division by a scalar multiplies by the reciprocal, which differs by one ulp from the IEEE
+    division the reference performs on the CPU."""
+    p = grid_coord_proj.detach().cpu()
+    g = torch.zeros_like(p)
+    g[:, 0] = 2 * (p[:, 0] / heatmap_shape[1] - 0.5)
+    g[:, 1] = 2 * (p[:, 1] / heatmap_shape[0] - 0.5)
+    g = g.to(grid_coord_proj.device)
     return g.unsqueeze(1).unsqueeze(0).expand(batch_size, -1, -1, -1)
 
 

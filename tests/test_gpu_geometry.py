@@ -51,7 +51,7 @@ def test_project_voxels_raises_on_axis(cam):
         _lib.project_voxels(cam.calib_struct(1280, 1024), 33, 2.0, (1024, 1280), "cuda")   # odd V: voxel on the axis
 
 
-def _voxelize(cam, depth, V):
+def _voxelize(cam, depth, V, side=2.0):
     from sceneego_b200 import _lib
     ray = cam.ray_table_device(1280, 1024)
     d = torch.as_tensor(depth).float().cuda()
@@ -60,7 +60,7 @@ def _voxelize(cam, depth, V):
     occ = torch.zeros(d.shape[0], V, V, V, device="cuda")
     lay = _lib.vol_layout(V, 3, d.shape[0])
     buf = _lib.alloc_volume(lay, 48, "cuda")
-    _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, 2.0, occ, buf, lay, channel=32)
+    _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, side, occ, buf, lay, channel=32)
     planar = _lib.unpack_volume(buf, lay, d.shape[0], 40)[:, 32]
     assert torch.equal(planar, occ), "planar bf16 scene channel differs from the f32 grid"
     return occ.cpu().numpy()
@@ -103,6 +103,10 @@ def test_voxelize_edge_cases_vs_oracle(cam, tables64):
         ref = orc.voxelize_depth(d, tables64.ray, 64, 2.0)
         assert np.array_equal(_voxelize(cam, d, 64)[0], ref)
     assert _voxelize(cam, cases[0], 64)[0].sum() == 1.0
+    # cuboid sides that are not a power of two take the fp64-divide path (2.0 takes the exact-multiply path)
+    for side in (3.0, 1.7, 4.0):
+        for d in (cases[3], cases[4]):
+            assert np.array_equal(_voxelize(cam, d, 64, side)[0], orc.voxelize_depth(d, tables64.ray, 64, side)), side
 
 
 def test_voxelize_batch_consistency_full_size(cam, tables64):
@@ -166,6 +170,7 @@ def test_materialised_features_and_generic_grid_sample(tables64):
     assert (full.cpu() - ref_full).abs().max().item() <= 1e-4 * ref_full.abs().max().item()
     grid_b = op.get_grid_coord_proj_batch(tables64.grid_px.cuda(), 4, (1024, 1280))
     assert grid_b.shape == (4, 64 ** 3, 1, 2) and grid_b.stride(0) == 0
+    assert torch.equal(grid_b[0].cpu(), tables64.grid)       # bit-identical to the reference's CPU table
     lifted = op.unproject_heatmaps_one_view_batch(full, grid_b, 64)
     ref = orc.unproject(ref_full, tables64.grid.unsqueeze(0).expand(2, -1, -1, -1), 64)
     # inputs differ by the 256-term fp32 summation order of the 1x1 conv (GPU vs CPU)
@@ -175,7 +180,9 @@ def test_materialised_features_and_generic_grid_sample(tables64):
     assert (one - lifted[1:2]).abs().sum().item() == 0.0     # the reference's own loop==batch smoke check
     fused = torch.empty(2, 32, 64, 64, 64, device="cuda")
     _lib.unproject(feat32, tables64.grid.reshape(-1, 2).cuda().contiguous(), None, 64, 2.0, 1024, 1280, fused, None, None)
-    assert torch.allclose(fused, lifted, rtol=1e-5, atol=1e-5)
+    # same grid, same values, different association of the four products (fma chain vs sum)
+    d = (fused - lifted).abs().max().item()
+    assert ((fused - lifted).norm() / lifted.norm()).item() <= 1e-6 and d <= 1e-5 * lifted.abs().max().item(), d
 
 
 def test_generic_grid_sample_out_of_bounds():
