@@ -150,13 +150,20 @@ struct ConvParams {
   int tiles, L, WL;                 // tiles per item, positions per item, window length (positions)
   int n_items;
   int win_stages, w_slots, wchunk_taps, wchunks_per_dx;
+  int wrows;                        // 3^3 only: whole dy-rows per weight chunk (0 = generic tap loop)
   uint32_t win_bytes, wchunk_bytes, tap_bytes;
   uint32_t off_win, off_w, off_bias, off_bar;
   uint32_t tmem_cols, half_cols;
+  int debug;                        // SCENEEGO_DEBUG bit mask (tuning experiments only; 0 in production)
 };
 
 constexpr int CONV_EPI_WARPS = 8;
-constexpr int CONV_THREADS = 64 + 32 * CONV_EPI_WARPS;   // producer warp, MMA warp, 8 epilogue warps
+// One warp can issue a tcgen05.mma only every ~41.5 cycles (tools/mma_replay.cu), which is longer than
+// the tensor pipe needs for N <= 64 (48 cycles at N = 64).  The tiles of a work item are therefore
+// split over up to four issuing warps, one per SM sub-partition.
+__host__ __device__ constexpr int conv_mma_warps(int tiles) { return tiles >= 4 ? 4 : tiles; }
+__host__ __device__ constexpr int conv_threads(int tiles) { return 32 * (1 + conv_mma_warps(tiles) + CONV_EPI_WARPS); }
+constexpr int CONV_MAX_THREADS = 32 * (1 + 4 + CONV_EPI_WARPS);   // producer warp, <= 4 MMA warps, 8 epilogue warps
 constexpr int MAX_STAGES = 4, MAX_WSLOTS = 8;
 
 struct RowInfo {
@@ -297,8 +304,8 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& 
 // descriptors differ by constants: the single issuing lane must sustain one tcgen05.mma per
 // ~41 cycles (measured floor at N<=32, tools/mma_rate.cu).
 // ---------------------------------------------------------------------------
-template <int KSTEPS, int TILES, int XS>
-__global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+template <int KSTEPS, int TILES, int XS, int WROWS>
+__global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are
   // uniform branches and the MMA issuer's address arithmetic can live in uniform registers
@@ -314,11 +321,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             B_TMEM_FULL = 2 * MAX_STAGES + 2 * MAX_WSLOTS, B_TMEM_EMPTY = B_TMEM_FULL + 2, B_COUNT = B_TMEM_EMPTY + 2;
   uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
-  for (int i = threadIdx.x; i < p.n0; i += CONV_THREADS) s_bias[i] = p.bias[i];
+  constexpr int NW = conv_mma_warps(TILES);          // MMA-issuing warps: warps 1..NW
+  constexpr int FIRST_EPI = 1 + NW;                  // epilogue warps: FIRST_EPI .. FIRST_EPI+7
+  for (int i = threadIdx.x; i < p.n0; i += conv_threads(TILES)) s_bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), 1); mbar_init(BAR(B_EMPTY_WIN + i), 1); }
-    for (int i = 0; i < MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), 1); mbar_init(BAR(B_EMPTY_W + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), 1); mbar_init(BAR(B_TMEM_EMPTY + i), CONV_EPI_WARPS); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), 1); mbar_init(BAR(B_EMPTY_WIN + i), NW); }
+    for (int i = 0; i < MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), 1); mbar_init(BAR(B_EMPTY_W + i), NW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), NW); mbar_init(BAR(B_TMEM_EMPTY + i), CONV_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -349,31 +358,42 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     // ===================== producer =====================
     if (lane == 0) {
       int ws = 0, wph = 0, sl = 0, sph = 0;
+      int n_win_issued = 0, n_w_issued = 0;
       for (int it = 0; it < my_items; ++it) {
         int ib, ix0, icell0;
         const int64_t q0 = item_origin(blockIdx.x + it * gridDim.x, ib, ix0, icell0);
         for (int dx = 0; dx < p.n_dx; ++dx) {
           mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
+          if ((p.debug & 4) && n_win_issued >= p.win_stages) { mbar_arrive(BAR(B_FULL_WIN + ws)); }
+          else {
+          ++n_win_issued;
           mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * (2 * KSTEPS));
           const int64_t qs = q0 + (int64_t)(dx - p.r) * p.ls.pitch_x - halo;
 #pragma unroll
           for (int g = 0; g < 2 * KSTEPS; ++g)
             bulk_g2s(sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS + g) * p.win_bytes,
                      p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8, p.win_bytes, BAR(B_FULL_WIN + ws));
+          }
           if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
           for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
             mbar_wait(BAR(B_EMPTY_W + sl), sph ^ 1);
+            if ((p.debug & 2) && n_w_issued >= p.w_slots) { mbar_arrive(BAR(B_FULL_W + sl)); }
+            else {
+            ++n_w_issued;
             mbar_expect_tx(BAR(B_FULL_W + sl), p.wchunk_bytes);
             const char* wsrc = reinterpret_cast<const char*>(p.w) +
                                (size_t)(dx * p.wchunks_per_dx + wc) * p.wchunk_bytes;
             bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes, wsrc, p.wchunk_bytes, BAR(B_FULL_W + sl));
+            }
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp <= NW) {
+    // ===================== MMA issuers =====================
+    // Warp w issues the MMAs of tiles (w-1), (w-1)+NW, ...; every issuing warp commits to the
+    // window / weight / accumulator barriers, whose arrival counts are NW.
     // The whole warp runs this loop converged so that every descriptor is a warp-uniform value
     // (uniform registers, no per-MMA R2UR/ELECT loop); only the tcgen05 instructions themselves
     // are predicated on one elected lane, which is also the lane that commits.
@@ -393,12 +413,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     const uint32_t n_cols = (uint32_t)p.N;
     const int pitch_y = p.ls.pitch_y, ksz = p.k, wtaps = p.wchunk_taps;
     const uint32_t is_deconv = (uint32_t)p.deconv, par_cols = (uint32_t)p.n0;
+    const uint32_t my_tile = (uint32_t)(warp - 1);                             // first tile of this warp
+    const uint32_t a_mine = my_tile * 128u;                                    // its row offset, in 16-B cells
     int ws = 0, wph = 0, sl = 0, sph = 0;
     for (int it = 0; it < my_items; ++it) {
       const int buf = it & 1;
       mbar_wait_warp(BAR(B_TMEM_EMPTY + buf), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d0 = tmem_u + (uint32_t)buf * p.half_cols;
+      const uint32_t d_mine = tmem_u + (uint32_t)buf * p.half_cols + my_tile * n_cols;
       uint32_t acc = 0;
       for (int dx = 0; dx < p.n_dx; ++dx) {
         mbar_wait_warp(BAR(B_FULL_WIN + ws), wph);
@@ -410,21 +432,47 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           mbar_wait_warp(BAR(B_FULL_W + sl), sph);
           tc_fence_after();
           uint32_t b_lo = (((sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes) >> 4) & 0x3FFFu) | b_lo_flags;
-          for (int tt = 0; tt < wtaps; ++tt) {
-            const uint32_t a_lo = win_lo + (uint32_t)(dy * pitch_y + dz);      // tap shift, in 16-B cells
-            if (leader) {
+          if constexpr (WROWS == 0) {
+            // generic chunk: `wtaps` taps, tap coordinates carried in running counters
+            for (int tp = 0; tp < wtaps; ++tp) {
+              const uint32_t a_lo = win_lo + (uint32_t)(dy * pitch_y + dz);    // tap shift, in 16-B cells
+              if (leader && !(p.debug & 8)) {
 #pragma unroll
-              for (int t = 0; t < TILES; ++t) {
+                for (int tt = 0; tt < TILES / NW; ++tt) {
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks)
-                  tc_mma_bf16(d0 + (uint32_t)t * n_cols + dcol,
-                              desc_hi | (a_lo + (uint32_t)t * 128u + (uint32_t)ks * a_ks_step),
-                              desc_hi | (b_lo + (uint32_t)ks * b_ks_step), idesc, ks == 0 ? acc : 1u);
+                  for (int ks = 0; ks < KSTEPS; ++ks)
+                    tc_mma_bf16(d_mine + (uint32_t)(tt * NW) * n_cols + dcol,
+                                desc_hi | (a_lo + a_mine + (uint32_t)(tt * NW) * 128u + (uint32_t)ks * a_ks_step),
+                                desc_hi | (b_lo + (uint32_t)ks * b_ks_step), idesc, ks == 0 ? acc : 1u);
+                }
+              }
+              b_lo += b_tap_step;
+              if (is_deconv) { dcol += par_cols; }                             // next parity: fresh columns, acc stays 0
+              else { acc = 1; if (++dz == ksz) { dz = 0; ++dy; } }
+            }
+          } else {
+            // 3^3 stencil, chunk = WROWS whole dy-rows of 3 taps: straight-line code, the tap shifts are
+            // (dy + r) * pitch_y + j with compile-time r, j -- no per-tap loop control or divergence
+            if (leader && !(p.debug & 8)) {
+#pragma unroll
+              for (int r = 0; r < WROWS; ++r) {
+                const uint32_t a_row = win_lo + a_mine + (uint32_t)((dy + r) * pitch_y);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                  for (int tt = 0; tt < TILES / NW; ++tt) {
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks)
+                      tc_mma_bf16(d_mine + (uint32_t)(tt * NW) * n_cols,
+                                  desc_hi | (a_row + (uint32_t)j + (uint32_t)(tt * NW) * 128u + (uint32_t)ks * a_ks_step),
+                                  desc_hi | (b_lo + (uint32_t)(r * 3 + j) * b_tap_step + (uint32_t)ks * b_ks_step), idesc,
+                                  (ks == 0 && r == 0 && j == 0) ? acc : 1u);
+                  }
+                }
               }
             }
-            b_lo += b_tap_step;
-            if (is_deconv) { dcol += par_cols; }                               // next parity: fresh columns, acc stays 0
-            else { acc = 1; if (++dz == ksz) { dz = 0; ++dy; } }
+            acc = 1;
+            dy += WROWS;
           }
           if (leader) tc_commit(BAR(B_EMPTY_W + sl));
           if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
@@ -442,7 +490,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     // Eight warps: two per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31).  The pair
     // splits the item by tile parity (by column-chunk parity when the item is a single tile).
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - FIRST_EPI) >> 2;
     const int nch = p.N >> 4;
     const int S = p.ls.side;
     const int t_first = TILES >= 2 ? half : 0, t_step = TILES >= 2 ? 2 : 1;
@@ -488,7 +536,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       mbar_wait(BAR(B_TMEM_FULL + buf), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = t_first; t < TILES; t += t_step) {
+      for (int t = t_first; t < TILES && !(p.debug & 1); t += t_step) {
         RowInfo ri_next = ri;
         if (t + t_step < TILES) ri_next = row_info(t + t_step);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * p.half_cols +
@@ -522,20 +570,29 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 }
 
 typedef void (*conv_tc_fn)(const ConvParams);
-static conv_tc_fn pick_conv_tc(int ksteps, int tiles, int xs) {
-  if (xs == 4 && ksteps == 3 && tiles == 4) return conv_tc_kernel<3, 4, 4>;
-  if (xs == 4 && ksteps == 3 && tiles == 2) return conv_tc_kernel<3, 4 / 2, 4>;
-  if (xs == 4 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 4>;
-  if (xs == 2 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 2>;
-  if (xs == 2 && ksteps == 2 && tiles == 8) return conv_tc_kernel<2, 8, 2>;
-  if (xs == 2 && ksteps == 1 && tiles == 4) return conv_tc_kernel<1, 4, 2>;
-  if (xs == 2 && ksteps == 4 && tiles == 2) return conv_tc_kernel<4, 2, 2>;
+template <int WROWS>
+static conv_tc_fn pick_conv_tc_w(int ksteps, int tiles, int xs) {
+  if (xs == 4 && ksteps == 3 && tiles == 4) return conv_tc_kernel<3, 4, 4, WROWS>;
+  if (xs == 4 && ksteps == 3 && tiles == 2) return conv_tc_kernel<3, 2, 4, WROWS>;
+  if (xs == 4 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 4, WROWS>;
+  if (xs == 4 && ksteps == 2 && tiles == 2) return conv_tc_kernel<2, 2, 4, WROWS>;
+  if (xs == 2 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 2, WROWS>;
+  if (xs == 2 && ksteps == 1 && tiles == 4) return conv_tc_kernel<1, 4, 2, WROWS>;
+  if (xs == 2 && ksteps == 4 && tiles == 2) return conv_tc_kernel<4, 2, 2, WROWS>;
   if (xs != 1) return nullptr;
-#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T, 1>;
-  SE_CASE(1, 8) SE_CASE(2, 8) SE_CASE(3, 4) SE_CASE(3, 8) SE_CASE(2, 4) SE_CASE(4, 4) SE_CASE(4, 2) SE_CASE(8, 2)
-  SE_CASE(1, 4) SE_CASE(1, 2) SE_CASE(2, 2) SE_CASE(8, 1) SE_CASE(4, 1) SE_CASE(2, 1) SE_CASE(1, 1) SE_CASE(3, 2) SE_CASE(3, 1)
+#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T, 1, WROWS>;
+  SE_CASE(2, 4) SE_CASE(4, 4) SE_CASE(4, 2) SE_CASE(8, 2) SE_CASE(1, 4) SE_CASE(1, 2) SE_CASE(2, 2)
+  SE_CASE(8, 1) SE_CASE(4, 1) SE_CASE(2, 1) SE_CASE(1, 1) SE_CASE(1, 8) SE_CASE(2, 8)
+  if (WROWS == 0) {
+    SE_CASE(3, 4) SE_CASE(3, 8) SE_CASE(3, 2) SE_CASE(3, 1)
+  }
 #undef SE_CASE
   return nullptr;
+}
+static conv_tc_fn pick_conv_tc(int ksteps, int tiles, int xs, int wrows) {
+  if (wrows == 3) return pick_conv_tc_w<3>(ksteps, tiles, xs);
+  if (wrows == 1) return pick_conv_tc_w<1>(ksteps, tiles, xs);
+  return pick_conv_tc_w<0>(ksteps, tiles, xs);
 }
 
 // ---------------------------------------------------------------------------
@@ -674,20 +731,31 @@ static bool try_plan(ConvParams& p, int tiles, int want_stages) {
   const int WL = L + 2 * p.r * (p.ls.pitch_y + 1);
   const uint32_t win_bytes = (uint32_t)WL * 16u;
   const uint32_t stage = win_bytes * p.cin_planes;
-  // weight chunk: as many taps of one dx as fit ~24 KB, must divide k*k
-  int wct = taps_dx;
-  while (wct > 1 && (uint32_t)wct * p.tap_bytes > 24576u) {
-    int nx = wct - 1;
-    while (nx > 1 && taps_dx % nx) --nx;
-    wct = nx;
-  }
-  const uint32_t wchunk = (uint32_t)wct * p.tap_bytes;
   const uint32_t fixed = 1024;  // bias + barriers + tmem ptr
-  if ((uint64_t)stage * want_stages + fixed + 2ull * wchunk > kMaxSmem) return false;
+  if ((uint64_t)stage * want_stages + fixed > kMaxSmem) return false;
   const uint32_t used = stage * want_stages + fixed;
-  int slots = (int)((kMaxSmem - used) / wchunk);
+  const uint32_t room = kMaxSmem - used;
+  // weight chunk.  3^3 stencils: whole dy-rows (3 taps) per chunk so the issue loop is straight-line
+  // code -- all 9 taps of a dx when three slots of that size fit, else one row; anything else: as many
+  // taps of one dx as fit ~24 KB (must divide the taps of a dx).
+  int wct = taps_dx, wrows = 0;
+  if (p.k == 3 && !p.deconv && 3u * 9u * p.tap_bytes <= room) { wct = 9; wrows = 3; }
+  else if (p.k == 3 && !p.deconv && 2u * 3u * p.tap_bytes <= room) { wct = 3; wrows = 1; }
+  else {
+    while (wct > 1 && (uint32_t)wct * p.tap_bytes > 24576u) {
+      int nx = wct - 1;
+      while (nx > 1 && taps_dx % nx) --nx;
+      wct = nx;
+    }
+  }
+  { const char* e = getenv("SCENEEGO_WCHUNK"); if (e && atoi(e) > 0 && taps_dx % atoi(e) == 0) { wct = atoi(e); wrows = (p.k == 3 && !p.deconv && wct % 3 == 0) ? wct / 3 : 0; if (wrows == 2) wrows = 0; } }
+  const uint32_t wchunk = (uint32_t)wct * p.tap_bytes;
+  if (2ull * wchunk > room) return false;
+  int slots = (int)(room / wchunk);
   if (slots > MAX_WSLOTS) slots = MAX_WSLOTS;
   if (slots > 4 && wchunk > 8192) slots = 4;
+  { const char* e = getenv("SCENEEGO_WSLOTS"); if (e && atoi(e) >= 2 && atoi(e) <= MAX_WSLOTS && (uint64_t)used + (uint64_t)atoi(e) * wchunk <= kMaxSmem) slots = atoi(e); }
+  p.wrows = wrows;
   p.tiles = tiles; p.L = L; p.WL = WL;
   p.win_bytes = win_bytes; p.win_stages = want_stages;
   p.wchunk_taps = wct; p.wchunks_per_dx = taps_dx / wct; p.wchunk_bytes = wchunk; p.w_slots = slots;
@@ -779,6 +847,7 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
   p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);
   p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
   p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
+  { const char* ed = getenv("SCENEEGO_DEBUG"); p.debug = ed ? atoi(ed) : 0; }
   const int smem = plan_conv(p);
   SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", op_index);
   if (p.xs == 1) {
@@ -789,21 +858,22 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
     p.n_items = batch * p.n_xg * p.items_per_plane;
   }
   const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  conv_tc_fn fn = pick_conv_tc(p.ksteps, p.tiles, p.xs);
-  SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d xs=%d", op_index, p.ksteps,
-             p.tiles, p.xs);
+  conv_tc_fn fn = pick_conv_tc(p.ksteps, p.tiles, p.xs, p.wrows);
+  if (fn == nullptr && p.wrows != 0) { p.wrows = 0; fn = pick_conv_tc(p.ksteps, p.tiles, p.xs, 0); }   // same chunking, generic tap loop
+  SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d xs=%d wrows=%d", op_index, p.ksteps,
+             p.tiles, p.xs, p.wrows);
   {
-    static conv_tc_fn configured[32];
+    static conv_tc_fn configured[96];
     static int n_configured = 0;
     bool done = false;
     for (int c = 0; c < n_configured; ++c) done |= (configured[c] == fn);
     if (!done) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
       if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-      if (n_configured < 32) configured[n_configured++] = fn;
+      if (n_configured < 96) configured[n_configured++] = fn;
     }
   }
-  fn<<<grid, CONV_THREADS, kMaxSmem, st>>>(p);
+  fn<<<grid, conv_threads(p.tiles), kMaxSmem, st>>>(p);
   SE_CUDA_LAUNCH_CHECK("conv_tc");
   ++g_launches;
   return SCENEEGO_OK;
