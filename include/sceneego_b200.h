@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCENEEGO_ABI_VERSION 1
+#define SCENEEGO_ABI_VERSION 2
 
 enum {
   SCENEEGO_OK = 0,
@@ -102,10 +102,18 @@ typedef struct sceneego_vol_layout {
   int32_t guard;         /* zero positions in front of every frame                      */
   int32_t frame_pitch;   /* guard + S*pitch_x                                           */
   int64_t plane_stride;  /* positions per channel-group plane (all frames + slack)      */
+  int32_t s2d;           /* 1: space-to-depth storage of a volume of side 2*S (stem input only):
+                            voxel (x,y,z), channel c lives in plane ((x&1)*4+(y&1)*2+(z&1))*(C/8)+c/8 at
+                            block position (x>>1,y>>1,z>>1); the occupancy channel (the one after the
+                            C feature channels) is ONE extra plane whose cell holds the 8 parity
+                            values of the 2x2x2 block as its 8 entries                     */
+  int32_t reserved;
 } sceneego_vol_layout_t;
 
 /* Fill a layout for (side, pad, batch); returns plane_stride (positions). */
 int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layout_t* out);
+/* Space-to-depth layout of a volume of side `full_side` (even): S = full_side/2, pad = 2, s2d = 1. */
+int64_t sceneego_vol_layout_make_s2d(int full_side, int batch, sceneego_vol_layout_t* out);
 
 /* Bilinear gather of the (virtually) x`scale`-upsampled, zero-padded feature map at the
  * projected voxel centres.  Replaces Upsample+ConstantPad2d (voxel_net_depth.py:60-61)
@@ -155,7 +163,8 @@ int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_layout_t* la
 
 /* ---- a7: V2V encoder-decoder (network/v2v.py) ------------------------------ */
 
-enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2 };
+enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2,
+       SCENEEGO_OP_STEM7_S2D = 3   /* Conv3d(33,16,k7)+BN+ReLU from an s2d source, network/v2v.py:147 */ };
 enum {
   SCENEEGO_F_RELU = 1,         /* ReLU after bias (+ residual)                              */
   SCENEEGO_F_RESIDUAL = 2,     /* add buffer `res` before the ReLU (Res3DBlock, v2v.py:40-43) */
@@ -190,6 +199,15 @@ int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const flo
                            const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
                            double eps, int cout, int cin, int ksize, int transposed, int cout_pad,
                            int cin_pad, int xstack, uint16_t* h_w_out, float* h_b_out);
+
+/* Same for the 7^3 stem read from a space-to-depth source (SCENEEGO_OP_STEM7_S2D):
+ *   h_weight (16,33,7,7,7) fp32.  Output: sceneego_v2v_stem_s2d_weight_bytes() bytes of bf16 in the
+ *   kernel's streaming order (2x2x2 output-stacked Toeplitz blocks per input offset, the occupancy
+ *   channel packed along K) and 16 fp32 biases. */
+size_t sceneego_v2v_stem_s2d_weight_bytes(void);
+int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
+                               const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
+                               double eps, uint16_t* h_w_out, float* h_b_out);
 
 /* Execute `n_ops` steps on `batch` frames.  d_blob: packed weights + biases. */
 int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,

@@ -21,7 +21,8 @@ SYMBOLS = [
     "sceneego_unproject_f32", "sceneego_voxelize_depth_f64", "sceneego_pack_volume_bf16",
     "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
-    "sceneego_world2camera_f32", "sceneego_grid_sample_f32",
+    "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
+    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d",
 ]
 
 
@@ -32,7 +33,8 @@ class Calib(C.Structure):
 
 class VolLayout(C.Structure):
     _fields_ = [("side", C.c_int32), ("pad", C.c_int32), ("pitch_y", C.c_int32), ("pitch_x", C.c_int32),
-                ("guard", C.c_int32), ("frame_pitch", C.c_int32), ("plane_stride", C.c_int64)]
+                ("guard", C.c_int32), ("frame_pitch", C.c_int32), ("plane_stride", C.c_int64),
+                ("s2d", C.c_int32), ("reserved", C.c_int32)]
 
 
 class V2VOp(C.Structure):
@@ -43,7 +45,7 @@ class V2VOp(C.Structure):
                 ("lay_src", VolLayout), ("lay_dst", VolLayout)]
 
 
-OP_CONV, OP_MAXPOOL2, OP_DECONV2 = 0, 1, 2
+OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D = 0, 1, 2, 3
 F_RELU, F_RESIDUAL, F_ADD_AFTER, F_OUT_F32 = 1, 2, 4, 8
 
 _lib = None
@@ -66,8 +68,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib = C.CDLL(p)
     lib.sceneego_last_error.restype = C.c_char_p
     lib.sceneego_vol_layout_make.restype = C.c_int64
+    lib.sceneego_vol_layout_make_s2d.restype = C.c_int64
+    lib.sceneego_v2v_stem_s2d_weight_bytes.restype = C.c_size_t
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
-    if lib.sceneego_abi_version() != 1:
+    if lib.sceneego_abi_version() != 2:
         raise SceneEgoError("libsceneego_b200.so ABI version mismatch")
     if path is None:
         _lib = lib
@@ -112,6 +116,15 @@ def vol_layout(side: int, pad: int, batch: int) -> VolLayout:
     rc = load_library().sceneego_vol_layout_make(int(side), int(pad), int(batch), C.byref(lay))
     if rc < 0:
         raise SceneEgoError("vol_layout_make: bad arguments")
+    return lay
+
+
+def vol_layout_s2d(full_side: int, batch: int) -> VolLayout:
+    """Space-to-depth layout of the stem input (8 parity sub-volumes of side full_side/2, pad 2)."""
+    lay = VolLayout()
+    rc = load_library().sceneego_vol_layout_make_s2d(int(full_side), int(batch), C.byref(lay))
+    if rc < 0:
+        raise SceneEgoError("vol_layout_make_s2d: bad arguments")
     return lay
 
 
@@ -207,7 +220,7 @@ def pack_volume(x: torch.Tensor, out_bf16: torch.Tensor, lay: VolLayout, c_offse
 
 
 def unpack_volume(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int) -> torch.Tensor:
-    s = lay.side
+    s = 2 * lay.side if lay.s2d else lay.side
     out = torch.empty(batch, channels, s, s, s, dtype=torch.float32, device=vol_bf16.device)
     _check(load_library().sceneego_unpack_volume_f32(_ptr(vol_bf16), C.byref(lay), batch, channels, _ptr(out),
                                                      _stream()), "unpack_volume")

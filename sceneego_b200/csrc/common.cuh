@@ -55,6 +55,27 @@ __device__ __forceinline__ float voxel_coord(float lo, float step, int i) {
   return __fadd_rn(lo, __fmul_rn(step, (float)i));
 }
 
+// Cell (16-byte group of 8 bf16) of voxel (x,y,z), channel group g of a C8-group feature volume; handles
+// the space-to-depth stem input (lay.s2d, include/sceneego_b200.h).
+__host__ __device__ inline int64_t vol_cell(const sceneego_vol_layout_t& L, int b, int x, int y, int z, int g, int C8) {
+  if (L.s2d) {
+    const int par = ((x & 1) << 2) | ((y & 1) << 1) | (z & 1);
+    return (int64_t)(par * C8 + g) * L.plane_stride + vol_pos(L, b, x >> 1, y >> 1, z >> 1);
+  }
+  return (int64_t)g * L.plane_stride + vol_pos(L, b, x, y, z);
+}
+// Element index (in bf16 units) of the occupancy channel that follows C8 feature groups.
+__host__ __device__ inline int64_t vol_scene_elem(const sceneego_vol_layout_t& L, int b, int x, int y, int z, int C8) {
+  if (L.s2d) {
+    const int par = ((x & 1) << 2) | ((y & 1) << 1) | (z & 1);
+    return ((int64_t)(8 * C8) * L.plane_stride + vol_pos(L, b, x >> 1, y >> 1, z >> 1)) * 8 + par;
+  }
+  return ((int64_t)C8 * L.plane_stride + vol_pos(L, b, x, y, z)) * 8;
+}
+
 constexpr int kNumSMs = 148;
+
+int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
+                    bool simt, cudaStream_t st);
 
 }  // namespace sceneego

@@ -275,18 +275,24 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
     for (int c = 0; c < C; ++c) __stcs(o + (size_t)c * N, acc[c]);
   }
   if (out_bf16) {
-    const int64_t pos = vol_pos(lay, b, vx, vy, vz);
+    const int64_t cell0 = vol_cell(lay, b, vx, vy, vz, 0, C / 8);
 #pragma unroll
     for (int g = 0; g < C / 8; ++g) {
       __align__(16) __nv_bfloat162 pk[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) pk[q] = __floats2bfloat162_rn(acc[8 * g + 2 * q], acc[8 * g + 2 * q + 1]);
-      *reinterpret_cast<uint4*>(out_bf16 + ((int64_t)g * lay.plane_stride + pos) * 8) =
+      *reinterpret_cast<uint4*>(out_bf16 + (cell0 + (int64_t)g * lay.plane_stride) * 8) =
           *reinterpret_cast<const uint4*>(pk);
     }
     // scene-occupancy plane(s) behind the features: cleared here, set by voxelize_kernel
-    for (int g = C / 8; g < C / 8 + extra_zero_planes; ++g)
-      *reinterpret_cast<uint4*>(out_bf16 + ((int64_t)g * lay.plane_stride + pos) * 8) = make_uint4(0, 0, 0, 0);
+    if (lay.s2d) {
+      // one cell per 2x2x2 block holds the block's 8 occupancy values: the even-even-even voxel clears it
+      if (extra_zero_planes > 0 && ((vx | vy | vz) & 1) == 0)
+        *reinterpret_cast<uint4*>(out_bf16 + (vol_scene_elem(lay, b, vx, vy, vz, C / 8) & ~(int64_t)7)) = make_uint4(0, 0, 0, 0);
+    } else {
+      for (int g = C / 8; g < C / 8 + extra_zero_planes; ++g)
+        *reinterpret_cast<uint4*>(out_bf16 + (cell0 + (int64_t)g * lay.plane_stride) * 8) = make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
@@ -354,16 +360,13 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
       const int c = (int)q0;
       if (occ_f32) occ_f32[(((size_t)b * V + c) * V + c) * V] = 1.0f;
       if (occ_bf16)
-        occ_bf16[((int64_t)(channel >> 3) * lay.plane_stride + vol_pos(lay, b, c, c, 0)) * 8 + (channel & 7)] =
-            __float2bfloat16(1.0f);
+        occ_bf16[vol_scene_elem(lay, b, c, c, 0, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
     }
   }
   if (ix >= 0) {
     if (occ_f32) occ_f32[(((size_t)b * V + ix) * V + iy) * V + iz] = 1.0f;
-    if (occ_bf16) {
-      const int64_t pos = vol_pos(lay, b, ix, iy, iz);
-      occ_bf16[((int64_t)(channel >> 3) * lay.plane_stride + pos) * 8 + (channel & 7)] = __float2bfloat16(1.0f);
-    }
+    if (occ_bf16)
+      occ_bf16[vol_scene_elem(lay, b, ix, iy, iz, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
   }
 }
 
@@ -372,39 +375,53 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------
 __global__ void pack_volume_kernel(const float* __restrict__ in, int c, int c_offset, __nv_bfloat16* __restrict__ out,
                                    sceneego_vol_layout_t lay) {
-  const int S = lay.side;
+  const int S = lay.s2d ? 2 * lay.side : lay.side;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= S * S * S) return;
   const int z = n % S, y = (n / S) % S, x = n / (S * S);
-  const int64_t pos = vol_pos(lay, b, x, y, z);
   for (int ch = 0; ch < c; ++ch) {
     const int oc = ch + c_offset;
-    out[((int64_t)(oc >> 3) * lay.plane_stride + pos) * 8 + (oc & 7)] =
-        __float2bfloat16(in[((size_t)b * c + ch) * S * S * S + n]);
+    const __nv_bfloat16 v = __float2bfloat16(in[((size_t)b * c + ch) * S * S * S + n]);
+    if (lay.s2d) {   // stem input: 32 feature channels (4 groups) + the occupancy channel (index 32)
+      if (oc < 32) out[vol_cell(lay, b, x, y, z, oc >> 3, 4) * 8 + (oc & 7)] = v;
+      else if (oc == 32) out[vol_scene_elem(lay, b, x, y, z, 4)] = v;
+    } else {
+      out[(vol_cell(lay, b, x, y, z, oc >> 3, 0)) * 8 + (oc & 7)] = v;
+    }
   }
 }
 
 __global__ void unpack_volume_kernel(const __nv_bfloat16* __restrict__ in, sceneego_vol_layout_t lay, int c,
                                      float* __restrict__ out) {
-  const int S = lay.side;
+  const int S = lay.s2d ? 2 * lay.side : lay.side;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= S * S * S) return;
   const int z = n % S, y = (n / S) % S, x = n / (S * S);
-  const int64_t pos = vol_pos(lay, b, x, y, z);
-  for (int ch = 0; ch < c; ++ch)
-    out[((size_t)b * c + ch) * S * S * S + n] =
-        __bfloat162float(in[((int64_t)(ch >> 3) * lay.plane_stride + pos) * 8 + (ch & 7)]);
+  for (int ch = 0; ch < c; ++ch) {
+    int64_t e;
+    if (lay.s2d) e = ch < 32 ? vol_cell(lay, b, x, y, z, ch >> 3, 4) * 8 + (ch & 7) : vol_scene_elem(lay, b, x, y, z, 4);
+    else e = vol_cell(lay, b, x, y, z, ch >> 3, 0) * 8 + (ch & 7);
+    out[((size_t)b * c + ch) * S * S * S + n] = __bfloat162float(in[e]);
+  }
 }
 
 }  // namespace sceneego
 
 using namespace sceneego;
 
+extern "C" int64_t sceneego_vol_layout_make_s2d(int full_side, int batch, sceneego_vol_layout_t* out) {
+  if (full_side <= 0 || (full_side & 1)) return SCENEEGO_E_INVALID;
+  const int64_t rc = sceneego_vol_layout_make(full_side / 2, 2, batch, out);
+  if (rc > 0) out->s2d = 1;
+  return rc;
+}
+
 extern "C" int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layout_t* out) {
   if (side <= 0 || pad < 0 || batch <= 0 || !out) return SCENEEGO_E_INVALID;
   sceneego_vol_layout_t L;
+  L.s2d = 0; L.reserved = 0;
   L.side = side;
   L.pad = pad;
   L.pitch_y = side + pad;
@@ -469,7 +486,7 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
                                       int extra_zero_planes, void* stream) {
   SE_REQUIRE(d_feat && (d_grid || calib) && (d_out_f32 || d_out_bf16), "unproject: null argument");
   SE_REQUIRE(c == 32, "unproject: 32 feature channels expected (process_features output)");
-  SE_REQUIRE(!d_out_bf16 || (lay && lay->side == V), "unproject: bf16 output needs a matching layout");
+  SE_REQUIRE(!d_out_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V), "unproject: bf16 output needs a matching layout");
   SE_REQUIRE(batch > 0 && batch <= 65535 && img_w >= img_h, "unproject: bad batch / image plane");
   const int N = V * V * V;
   dim3 grid((N + 127) / 128, batch);
@@ -495,7 +512,8 @@ extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int 
                                            void* stream) {
   SE_REQUIRE(d_depth && d_ray && (d_occ_f32 || d_occ_bf16), "voxelize: null argument");
   SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && img_w >= img_h, "voxelize: bad shape");
-  SE_REQUIRE(!d_occ_bf16 || (lay && lay->side == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
+  SE_REQUIRE(!d_occ_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
+  SE_REQUIRE(!d_occ_bf16 || !lay->s2d || channel % 8 == 0, "voxelize: s2d occupancy follows whole channel groups");
   dim3 grid((img_w + 255) / 256, img_h, batch);
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
   int e2 = 0;
@@ -513,7 +531,9 @@ extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int 
 extern "C" int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,
                                          const sceneego_vol_layout_t* lay, void* stream) {
   SE_REQUIRE(d_in && d_out && lay && batch > 0 && batch <= 65535, "pack_volume: bad argument");
-  const int N = lay->side * lay->side * lay->side;
+  const int S = lay->s2d ? 2 * lay->side : lay->side;
+  SE_REQUIRE(!lay->s2d || c + c_offset <= 33, "pack_volume: an s2d volume holds 32 feature channels + occupancy");
+  const int N = S * S * S;
   pack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>(d_in, c, c_offset,
                                                                                       (__nv_bfloat16*)d_out, *lay);
   SE_CUDA_LAUNCH_CHECK("pack_volume");
@@ -523,7 +543,9 @@ extern "C" int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, in
 extern "C" int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_layout_t* lay, int batch, int c,
                                           float* d_out, void* stream) {
   SE_REQUIRE(d_in && d_out && lay && batch > 0 && batch <= 65535, "unpack_volume: bad argument");
-  const int N = lay->side * lay->side * lay->side;
+  const int Sfull = lay->s2d ? 2 * lay->side : lay->side;
+  SE_REQUIRE(!lay->s2d || c <= 33, "unpack_volume: an s2d volume holds 32 feature channels + occupancy");
+  const int N = Sfull * Sfull * Sfull;
   unpack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_in,
                                                                                         *lay, c, d_out);
   SE_CUDA_LAUNCH_CHECK("unpack_volume");

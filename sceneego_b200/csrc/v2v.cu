@@ -20,7 +20,7 @@
 //   smem operands use the no-swizzle K-major canonical layout: 8 rows x 16 B core matrices,
 //   SBO = 128 B between 8-row groups, LBO = plane stride between the two K chunks.
 //   Accumulators: 2 x (tiles x N) fp32 columns of TMEM, double-buffered across work items.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,101 +29,8 @@
 namespace sceneego {
 
 // ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("sceneego conv_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-// Warp-converged variant: the loop condition is a warp vote, so control flow stays uniform and
-// ptxas keeps the MMA issuer's descriptor arithmetic in uniform registers.
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-    if (++spins > (1u << 26)) __trap();   // protocol bug: fail loudly instead of hanging the GPU
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (sm_100 format, version 1).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-
-// ---------------------------------------------------------------------------
 // conv parameters
 // ---------------------------------------------------------------------------
-// Division by a runtime constant via a 48-bit reciprocal: exact while n * d < 2^48 (host-checked).
-struct FastDiv { uint64_t m; uint32_t d; };
-static inline FastDiv make_fastdiv(uint32_t d) { FastDiv f; f.d = d; f.m = (1ull << 48) / d + 1; return f; }
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)n * f.m) >> 48); }
 
 struct ConvParams {
   const __nv_bfloat16* src;
@@ -214,21 +121,6 @@ __device__ __forceinline__ RowInfo decode_row_plane(const ConvParams& p, int b, 
   ri.n = (x * S + y) * S + z;
   ri.dpos = (int64_t)b * p.ld.frame_pitch + p.ld.guard + (int64_t)x * p.ld.pitch_x + (int64_t)y * p.ld.pitch_y + z;
   return ri;
-}
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x; f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  __align__(16) __nv_bfloat162 h[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return *reinterpret_cast<const uint4*>(h);
 }
 
 // Shared epilogue: v[0..15] are output channels c0..c0+15 of one row; r0/r1 hold the residual
@@ -713,16 +605,6 @@ void set_error(const char* fmt, ...) {
 }
 static thread_local int g_launches = 0;
 
-static uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-
-constexpr uint32_t kMaxSmem = 232448;  // 227 KB
-
 // Choose tiles / stages / weight chunking for a conv and fill the kernel parameters.
 // SCENEEGO_TILES / SCENEEGO_STAGES override the choice (tuning only).
 static bool try_plan(ConvParams& p, int tiles, int want_stages) {
@@ -903,6 +785,12 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
       dim3 grid((So * So * So + 255) / 256, op.cin / 8, batch);
       maxpool2_kernel<<<grid, 256, 0, st>>>(p.src, p.dst, p.ls, p.ld, op.cin / 8);
       SE_CUDA_LAUNCH_CHECK("maxpool2");
+      ++g_launches;
+      continue;
+    }
+    if (op.type == SCENEEGO_OP_STEM7_S2D) {
+      const int rc = launch_stem_s2d(op, d_buffers, d_blob, batch, i, op.impl == 1 || force_simt, st);
+      if (rc != SCENEEGO_OK) return rc;
       ++g_launches;
       continue;
     }

@@ -100,7 +100,10 @@ class _Program:
         self.blob_bytes = 0
         self.in_channels = in_channels
         self.in_pad = _pad16(in_channels)
-        self.lay_in = _lib.vol_layout(side, 3, chunk)          # stem input: 7^3 stencil needs 3 zero cells
+        # stem input.  33 channels (32 lifted features + occupancy): space-to-depth storage read by the
+        # 2x2x2-stacked stem kernel (csrc/stem.cu); anything else: plain layout, 7^3 stencil needs 3 zero cells
+        self.s2d = in_channels == 33
+        self.lay_in = _lib.vol_layout_s2d(side, chunk) if self.s2d else _lib.vol_layout(side, 3, chunk)
         self.lays = [_lib.vol_layout(side >> l, 1, chunk) for l in range(6)]
         self.level_channels = EncoderDecorder.CHANNELS
         self.in_buf = self._new_buffer(-1)
@@ -111,7 +114,8 @@ class _Program:
     # -- buffers -------------------------------------------------------------
     def _new_buffer(self, level: int) -> int:
         if level < 0:
-            t = _lib.alloc_volume(self.lay_in, self.in_pad, self.device)
+            # s2d: 8 parity sub-volumes x 4 channel groups + 1 plane of occupancy blocks
+            t = _lib.alloc_volume(self.lay_in, 33 * 8 if self.s2d else self.in_pad, self.device)
         else:
             t = _lib.alloc_volume(self.lays[level], self.level_channels[level], self.device)
         self.buffers.append(t)
@@ -187,6 +191,34 @@ class _Program:
         self.flops += fl
         self.meta.append(dict(kind="conv", cin=conv.in_channels, cout=conv.out_channels, k=k,
                               side=op.lay_src.side, flops=fl))
+
+    def stem_s2d(self, conv: nn.Conv3d, bn, src: int, dst: int):
+        """7^3 stem from the space-to-depth input (SCENEEGO_OP_STEM7_S2D)."""
+        lib = _lib.load_library()
+        assert conv.in_channels == 33 and conv.out_channels == 16 and conv.kernel_size[0] == 7
+        w = conv.weight.detach().float().cpu().contiguous().numpy()
+        bias = conv.bias.detach().float().cpu().contiguous().numpy() if conv.bias is not None else None
+        w_out = np.zeros(lib.sceneego_v2v_stem_s2d_weight_bytes() // 2, dtype=np.uint16)
+        b_out = np.zeros(16, dtype=np.float32)
+
+        def fp(a):
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        g = bn.weight.detach().float().cpu().contiguous().numpy()
+        bt = bn.bias.detach().float().cpu().contiguous().numpy()
+        mu = bn.running_mean.detach().float().cpu().contiguous().numpy()
+        var = bn.running_var.detach().float().cpu().contiguous().numpy()
+        _lib._check(lib.sceneego_v2v_pack_stem_s2d(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var), C.c_double(float(bn.eps)),
+                                                   fp(w_out), fp(b_out)), "v2v_pack_stem_s2d")
+        op = _lib.V2VOp()
+        op.type, op.flags = _lib.OP_STEM7_S2D, _lib.F_RELU
+        op.ksize, op.cin, op.cout, op.cout_real = 7, 33, 16, 16
+        op.src, op.dst, op.res, op.impl, op.xstack = src, dst, -1, 0, 1
+        op.w_offset, op.b_offset = self._append_blob(w_out), self._append_blob(b_out)
+        op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
+        self.ops.append(op)
+        fl = 2 * 33 * 16 * 343 * op.lay_dst.side ** 3
+        self.flops += fl
+        self.meta.append(dict(kind="conv", cin=33, cout=16, k=7, side=op.lay_dst.side, flops=fl))
 
     def pool(self, src: int, dst: int, channels: int):
         op = _lib.V2VOp()
@@ -279,8 +311,11 @@ class V2VModel(nn.Module):
         x = pg.acquire(0)
         # 7^3 stem, Cout = 16: the worst tcgen05 shape (N = 16 costs as much as N = 32 per MMA), so four
         # adjacent x-planes of outputs are stacked into N = 64 (tools/mma_rate.cu for the cost model)
-        pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True,
-                xstack=self.stem_xstack)
+        if pg.s2d:
+            pg.stem_s2d(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x)
+        else:
+            pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True,
+                    xstack=self.stem_xstack)
         for i in (1, 2, 3):
             y = self._res(pg, self.front_layers[i], x, 0)
             pg.release(x)

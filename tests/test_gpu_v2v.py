@@ -111,6 +111,30 @@ def test_x_stacked_conv(cin, cout, k, S, B, pad_src, xs):
     assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
 
 
+@pytest.mark.parametrize("V,B", [(16, 2), (32, 3), (64, 1)])
+def test_stem_s2d(V, B):
+    """7^3 stem from the space-to-depth input: 2x2x2 output stacking, occupancy packed along K."""
+    from sceneego_b200 import _lib
+    conv, bn = _mk_conv(33, 16, 7, seed=5)
+    g = torch.Generator().manual_seed(V + B)
+    x = util.bf16_round(torch.randn(B, 33, V, V, V, generator=g))
+    x[:, 32] = (x[:, 32] > 0.8).float()                       # occupancy channel is {0,1}
+    x = x.cuda()
+    got, dst, lay, src, lay_s = util.run_stem_s2d(x, conv, bn, impl=0)
+    assert torch.equal(_lib.unpack_volume(src, lay_s, B, 33), x)          # s2d pack/unpack round trip (bf16-exact input)
+    _close(got, _ref(x, conv, bn, True), f"stem s2d V{V}")
+    simt, _, _, _, _ = util.run_stem_s2d(x, conv, bn, impl=1)
+    assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()      # same blob, other summation order
+    plane = dst[0].float()
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(V, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
+
+
 @pytest.mark.parametrize("cin,cout,S,B", [(32, 32, 16, 2), (128, 128, 4, 2), (16, 32, 32, 1)])
 def test_tc_matches_simt_bitwise_close(cin, cout, S, B):
     """Same packed weights, same bf16 inputs: tensor-core and CUDA-core paths may differ only

@@ -31,9 +31,13 @@ def test_program_structure_and_flops():
     assert abs(V2VModel(32, 15).flops_per_frame(64) / 1e9 - 296.2) < 0.1
     pg = m.program(32, 2, torch.device("cpu"))
     kinds = [op.type for op in pg.ops]
-    assert kinds.count(_lib.OP_CONV) == 47 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
+    assert kinds.count(_lib.OP_CONV) == 46 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
+    assert kinds[0] == _lib.OP_STEM7_S2D
     assert pg.flops * 8 == m.flops_per_frame(64)
-    assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 48 and pg.ops[0].cout == 16 and pg.ops[0].lay_src.pad == 3
+    assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 33 and pg.ops[0].cout == 16
+    assert pg.ops[0].lay_src.s2d == 1 and pg.ops[0].lay_src.side == 16 and pg.ops[0].lay_src.pad == 2
+    pg32 = V2VModel(32, 15).program(32, 1, torch.device("cpu"))          # no occupancy channel: plain x-stacked stem
+    assert pg32.ops[0].type == _lib.OP_CONV and pg32.ops[0].cin == 32 and pg32.ops[0].lay_src.pad == 3
     last = pg.ops[-1]
     assert last.flags & _lib.F_OUT_F32 and last.cout_real == 15 and last.cout == 16
     # every op reads a buffer some earlier op (or the input staging) wrote, and never its own output
@@ -104,3 +108,61 @@ def test_config_and_synth():
     b = synth.synthetic_state_dict(list(reversed(util.stage_shapes())), seed=0)
     assert all(torch.equal(a[k], b[k]) for k in a)                    # order independent
     assert torch.equal(synth.synthetic_features(1), synth.synthetic_features(1))
+
+
+def test_stem_s2d_packing_reproduces_conv3d():
+    """The 2x2x2-stacked, occupancy-along-K weight blob of the s2d stem (csrc/stem.cu), walked on the
+    CPU in the kernel's streaming order over an s2d-arranged input, equals Conv3d(33,16,7,pad 3) + BN."""
+    lib = _lib.load_library()
+    torch.manual_seed(3)
+    conv = nn.Conv3d(33, 16, 7, padding=3)
+    bn = nn.BatchNorm3d(16).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1); bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 2)
+    w_out = np.zeros(lib.sceneego_v2v_stem_s2d_weight_bytes() // 2, dtype=np.uint16)
+    b_out = np.zeros(16, dtype=np.float32)
+    fp = lambda a: a.detach().float().contiguous().numpy().ctypes.data_as(C.c_void_p)
+    arrs = [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    keep = [a.detach().float().contiguous().numpy() for a in arrs]
+    ptrs = [k.ctypes.data_as(C.c_void_p) for k in keep]
+    assert lib.sceneego_v2v_pack_stem_s2d(*ptrs, C.c_double(bn.eps), w_out.ctypes.data_as(C.c_void_p),
+                                          b_out.ctypes.data_as(C.c_void_p)) == 0
+    wf = torch.from_numpy((w_out.astype(np.uint32) << 16).view(np.float32).copy()).double()   # bf16 -> f64
+    V, S2, P = 8, 4, 2
+    x = torch.randn(33, V, V, V).double()
+    x[32] = (x[32] > 0.5).double()
+    # s2d arrangement with pad 2: sub[par][c][X+P][Y+P][Z+P]
+    sub = torch.zeros(8, 33, S2 + 2 * P + 1, S2 + 2 * P + 1, S2 + 2 * P + 1, dtype=torch.float64)
+    for par in range(8):
+        px, py, pz = par >> 2, (par >> 1) & 1, par & 1
+        sub[par, :, P:P + S2, P:P + S2, P:P + S2] = x[:, px::2, py::2, pz::2]
+    acc = torch.zeros(S2, S2, S2, 128, dtype=torch.float64)
+    win = lambda par, c0, c1, bx, by, bz: sub[par, c0:c1, P + bx:P + bx + S2, P + by:P + by + S2, P + bz:P + bz + S2]
+    chunk = 16384 // 2
+    for s in range(32):
+        ox, py, pz = (s >> 2) - 3, (s >> 1) & 1, s & 1
+        par, bx = ((ox & 1) << 2) | (s & 3), ox >> 1
+        for tp in range(16):
+            by, bz = (tp >> 2) - 1 - py, (tp & 3) - 1 - pz
+            B = wf[s * 8 * chunk + tp * 4096: s * 8 * chunk + (tp + 1) * 4096].reshape(4, 128, 8)     # [kchunk][n][8]
+            A = win(par, 0, 32, bx, by, bz).reshape(4, 8, S2, S2, S2)
+            acc += torch.einsum("gcxyz,gnc->xyzn", A, B)
+    for s in range(5):
+        bx = s - 2
+        for tp in range(15):
+            by, bz0 = tp // 3 - 2, (tp % 3) * 2 - 2
+            base = (256 + s * 4) * chunk + tp * 2048
+            B = wf[base: base + 2048].reshape(2, 128, 8)
+            for c2 in range(2):
+                A = torch.stack([win(par, 32, 33, bx, by, bz0 + c2)[0] for par in range(8)])           # (8 parities, X, Y, Z)
+                acc += torch.einsum("exyz,ne->xyzn", A, B[c2])
+    out = torch.zeros(16, V, V, V, dtype=torch.float64)
+    for n0 in range(8):
+        sx, sy, sz = n0 >> 2, (n0 >> 1) & 1, n0 & 1
+        out[:, sx::2, sy::2, sz::2] = acc[..., n0 * 16:(n0 + 1) * 16].permute(3, 0, 1, 2)
+    out += torch.from_numpy(b_out).double()[:, None, None, None]
+    with torch.no_grad():
+        ref = bn.double()(conv.double()(x[None]))[0]
+    assert (out - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()      # bf16 weights (2^-9 relative each)
+    # and the blob's non-zero count is exactly the 343 x 33 x 16 taps, each stored once per stacked voxel it serves
+    assert int((w_out != 0).sum()) <= 343 * 33 * 16 * 8

@@ -84,5 +84,35 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     return _lib.unpack_volume(dst, lay_d, B, conv.out_channels), dst, lay_d
 
 
+def run_stem_s2d(x, conv, bn, impl=0):
+    """Run the 7^3 stem op (SCENEEGO_OP_STEM7_S2D) on x (B,33,V,V,V) f32 cuda; returns (B,16,V,V,V) f32."""
+    from sceneego_b200 import _lib
+    from sceneego_b200.network.v2v import _Program
+    B, V = x.shape[0], x.shape[2]
+    pg = _Program.__new__(_Program)
+    pg.side, pg.chunk, pg.device = V, B, x.device
+    pg.ops, pg.buffers, pg.buf_level, pg.free, pg.blob_parts, pg.blob_bytes = [], [], [], {}, [], 0
+    pg.flops, pg.meta = 0, []
+    lay_s = _lib.vol_layout_s2d(V, B)
+    lay_d = _lib.vol_layout(V, 1, B)
+    src = _lib.alloc_volume(lay_s, 33 * 8, x.device)
+    dst = _lib.alloc_volume(lay_d, 16, x.device)
+    _lib.pack_volume(x.contiguous(), src, lay_s)
+    lays = [lay_s, lay_d]
+    pg.buffers = [src, dst]
+    pg.buf_level = [0, 0]
+    pg.lay_of = lambda i: lays[i]
+    pg.stem_s2d(conv, bn, 0, 1)
+    pg.ops[0].impl = impl
+    pg.finalize()
+    global LAST_PROGRAM
+    LAST_PROGRAM = pg
+    lib = _lib.load_library()
+    rc = lib.sceneego_v2v_run(pg.op_array, 1, pg.buf_ptrs, C.c_void_p(pg.blob.data_ptr()), B, _lib._stream())
+    _lib._check(rc, "v2v_run")
+    torch.cuda.synchronize()
+    return _lib.unpack_volume(dst, lay_d, B, 16), dst, lay_d, src, lay_s
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_v2v.py tests/test_gpu_stage.py -m gpu -q --timeout 300 -p no:cacheprovider -x -k "not simt and not maxpool" 2>&1 | tail -n 8 > gpurun_out/quick_tests.log
-tail -n 4 gpurun_out/quick_tests.log
-./tools/mma_replay > gpurun_out/mma_replay.txt 2>&1; cat gpurun_out/mma_replay.txt
-for d in 1 7; do SCENEEGO_DEBUG=$d timeout 120 python tools/debug_conv.py one 2>&1 | head -3; done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 60 -c 2 -o gpurun_out/prof_conv_tc2 python tools/run_v2v_only.py 16 2 > gpurun_out/ncu_full.log 2>&1
-tail -n 2 gpurun_out/ncu_full.log
+timeout 900 python -m pytest tests/test_gpu_v2v.py -m gpu -q --timeout 600 -p no:cacheprovider -x -k "stem_s2d" 2>&1 | tail -n 15 > gpurun_out/stem_tests.log
+tail -n 15 gpurun_out/stem_tests.log
+timeout 900 python -m pytest tests/test_gpu_v2v.py tests/test_gpu_stage.py tests/test_gpu_geometry.py -m gpu -q --timeout 600 -p no:cacheprovider -k "not stem_s2d and not simt" 2>&1 | tail -n 12 > gpurun_out/quick_tests.log
+tail -n 12 gpurun_out/quick_tests.log
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-ops gpurun_out/v2v_ops.json > gpurun_out/bench.json 2> gpurun_out/bench.err
+cut -c 1-300 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
