@@ -164,7 +164,11 @@ int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_layout_t* la
 /* ---- a7: V2V encoder-decoder (network/v2v.py) ------------------------------ */
 
 enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2,
-       SCENEEGO_OP_STEM7_S2D = 3   /* Conv3d(33,16,k7)+BN+ReLU from an s2d source, network/v2v.py:147 */ };
+       SCENEEGO_OP_STEM7_S2D = 3,  /* Conv3d(33,16,k7)+BN+ReLU from an s2d source, network/v2v.py:147 */
+       SCENEEGO_OP_TAIL_MLP = 4    /* back_layers[1], back_layers[2] and output_layer (three 1x1 convs,
+                                      network/v2v.py:150-161,168-169) in one pass; blob segment at w_offset:
+                                      [w1 32x32][w2 32x32][w3 32x16] bf16 (pack_conv layout), then
+                                      [b1 32][b2 32][b3 16] f32; dst = (B,cout_real,S,S,S) f32 */ };
 enum {
   SCENEEGO_F_RELU = 1,         /* ReLU after bias (+ residual)                              */
   SCENEEGO_F_RESIDUAL = 2,     /* add buffer `res` before the ReLU (Res3DBlock, v2v.py:40-43) */

@@ -45,7 +45,7 @@ class V2VOp(C.Structure):
                 ("lay_src", VolLayout), ("lay_dst", VolLayout)]
 
 
-OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D = 0, 1, 2, 3
+OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D, OP_TAIL_MLP = 0, 1, 2, 3, 4
 F_RELU, F_RESIDUAL, F_ADD_AFTER, F_OUT_F32 = 1, 2, 4, 8
 
 _lib = None

@@ -1,0 +1,212 @@
+// a7, last three layers: Basic3DBlock(32,32,1) x 2 + Conv3d(32,15,1) (network/v2v.py:150-161,168-169)
+// fused into one pass.  A per-voxel 32 -> 32 -> 32 -> 15 MLP is HBM-bound (read 16.8 MB of bf16
+// activations, write 15.7 MB of f32 logits per 64^3 frame; 1.3 GFLOP), so the point is to touch
+// memory once: three separate 1x1 launches cost 29.6 us/frame on B200, the compulsory traffic is 5 us.
+// The intermediates never leave registers: the fp32 accumulator fragment of mma.sync.m16n8k16 has
+// exactly the thread layout of the next layer's bf16 A fragment (two n8 tiles = one k16 tile), so
+// bias + ReLU + bf16 rounding happen in place -- the same roundings as the unfused chain.
+// (Warp-level mma.sync rather than tcgen05: the chain of three dependent GEMMs per 16 rows is
+// latency-, not throughput-bound, and needs no shared-memory round trips this way.)
+#include "tc_common.cuh"
+
+namespace sceneego {
+
+struct TailParams {
+  const __nv_bfloat16* src;   // 32 channels = 4 planes, layout ls
+  float* dst;                 // (B, cout_real, S, S, S) f32
+  const __nv_bfloat16* w1;    // [4][32][8]   (sceneego_v2v_pack_conv layout, one tap)
+  const __nv_bfloat16* w2;    // [4][32][8]
+  const __nv_bfloat16* w3;    // [4][16][8]
+  const float *b1, *b2, *b3;  // 32, 32, 16
+  sceneego_vol_layout_t ls;
+  int batch, cout_real;
+  int64_t n_pos;              // positions to scan, starting at ls.guard
+  FastDiv fd_frame, fd_px, fd_py;
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// B fragments of a [cin/8][cout][8] weight block: thread (g = lane/4, q = lane%4) of n-tile nt, k-tile kt holds
+// (k = 16kt + 2q, +1; n = 8nt + g) and (k = 16kt + 8 + 2q, +1; n = 8nt + g).
+template <int NT>
+__device__ __forceinline__ void load_b(const __nv_bfloat16* w, int cout, int g, int q, uint32_t (&b)[NT][2][2]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      b[nt][kt][0] = *reinterpret_cast<const uint32_t*>(w + ((size_t)(2 * kt) * cout + nt * 8 + g) * 8 + 2 * q);
+      b[nt][kt][1] = *reinterpret_cast<const uint32_t*>(w + ((size_t)(2 * kt + 1) * cout + nt * 8 + g) * 8 + 2 * q);
+    }
+}
+
+// One hidden layer on a 16-row tile: a (2 k-tiles) -> relu(a W^T + bias) as the next layer's A fragments.
+__device__ __forceinline__ void hidden_layer(const uint32_t (&a)[2][4], const uint32_t (&b)[4][2][2],
+                                             const float (&bias)[4][2], uint32_t (&out)[2][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    float c[4] = {bias[nt][0], bias[nt][1], bias[nt][0], bias[nt][1]};
+    mma_bf16_16816(c, a[0], b[nt][0][0], b[nt][0][1]);
+    mma_bf16_16816(c, a[1], b[nt][1][0], b[nt][1][1]);
+    // accumulator (rows g / g+8, cols 8nt + 2q, +1) == A fragment slots of k-tile nt/2: even nt -> a0,a1; odd -> a2,a3
+    out[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+    out[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+  }
+}
+
+__global__ void __launch_bounds__(256) tail_mlp_kernel(const __grid_constant__ TailParams p) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  uint32_t B1[4][2][2], B2[4][2][2], B3[2][2][2];
+  load_b<4>(p.w1, 32, g, q, B1);
+  load_b<4>(p.w2, 32, g, q, B2);
+  load_b<2>(p.w3, 16, g, q, B3);
+  float bias1[4][2], bias2[4][2], bias3[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    bias1[nt][0] = p.b1[nt * 8 + 2 * q]; bias1[nt][1] = p.b1[nt * 8 + 2 * q + 1];
+    bias2[nt][0] = p.b2[nt * 8 + 2 * q]; bias2[nt][1] = p.b2[nt * 8 + 2 * q + 1];
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) { bias3[nt][0] = p.b3[nt * 8 + 2 * q]; bias3[nt][1] = p.b3[nt * 8 + 2 * q + 1]; }
+
+  const int S = p.ls.side;
+  const size_t N3 = (size_t)S * S * S;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n_chunks = (p.n_pos + 31) / 32;
+  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(p.src);
+  const int64_t plane32 = p.ls.plane_stride * 4;          // plane stride in 4-byte words
+  for (int64_t ch = warp_global; ch < n_chunks; ch += n_warps) {
+    const int64_t q0 = (int64_t)p.ls.guard + ch * 32;
+    // A fragments of both 16-row tiles: rows (g, g+8) of tile t, 4-byte word q of the row's cell in plane 2kt / 2kt+1
+    uint32_t a[2][2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        const int64_t w0 = (q0 + t * 16 + g) * 4 + q + (int64_t)(2 * kt) * plane32;
+        a[t][kt][0] = __ldcs(src32 + w0);
+        a[t][kt][1] = __ldcs(src32 + w0 + 8 * 4);
+        a[t][kt][2] = __ldcs(src32 + w0 + plane32);
+        a[t][kt][3] = __ldcs(src32 + w0 + plane32 + 8 * 4);
+      }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      uint32_t h1[2][4], h2[2][4];
+      hidden_layer(a[t], B1, bias1, h1);
+      hidden_layer(h1, B2, bias2, h2);
+      float c[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        c[nt][0] = bias3[nt][0]; c[nt][1] = bias3[nt][1]; c[nt][2] = bias3[nt][0]; c[nt][3] = bias3[nt][1];
+        mma_bf16_16816(c[nt], h2[0], B3[nt][0][0], B3[nt][0][1]);
+        mma_bf16_16816(c[nt], h2[1], B3[nt][1][0], B3[nt][1][1]);
+      }
+      // rows g and g+8 of this tile -> (frame, voxel); pads and guards are skipped
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t pos = (uint32_t)(q0 + t * 16 + g + 8 * r);
+        const uint32_t b = fdiv(pos, p.fd_frame);
+        const int rem = (int)(pos - b * (uint32_t)p.ls.frame_pitch) - p.ls.guard;
+        if ((int)b >= p.batch || rem < 0) continue;
+        const int x = (int)fdiv((uint32_t)rem, p.fd_px);
+        const int r2 = rem - x * p.ls.pitch_x;
+        const int y = (int)fdiv((uint32_t)r2, p.fd_py);
+        const int z = r2 - y * p.ls.pitch_y;
+        if (x >= S || y >= S || z >= S) continue;
+        float* o = p.dst + (size_t)b * p.cout_real * N3 + ((size_t)x * S + y) * S + z;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int col = nt * 8 + 2 * q + j;
+            if (col < p.cout_real) __stcs(o + (size_t)col * N3, c[nt][2 * r + j]);
+          }
+      }
+    }
+  }
+}
+
+// CUDA-core checker (op.impl = 1): one thread per voxel, same packed weights, same bf16 roundings.
+__global__ void __launch_bounds__(128) tail_mlp_simt_kernel(const __grid_constant__ TailParams p) {
+  const int S = p.ls.side;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= S * S * S) return;
+  const int z = n % S, y = (n / S) % S, x = n / (S * S);
+  const int64_t pos = vol_pos(p.ls, b, x, y, z);
+  float h[32], t[32];
+  for (int gq = 0; gq < 4; ++gq) {
+    float a[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)gq * p.ls.plane_stride + pos) * 8), a);
+    for (int i = 0; i < 8; ++i) h[gq * 8 + i] = a[i];
+  }
+  for (int layer = 0; layer < 2; ++layer) {
+    const __nv_bfloat16* w = layer ? p.w2 : p.w1;
+    const float* bias = layer ? p.b2 : p.b1;
+    for (int co = 0; co < 32; ++co) {
+      float acc = 0.f;
+      for (int ci = 0; ci < 32; ++ci) acc = fmaf(h[ci], __bfloat162float(w[((size_t)(ci >> 3) * 32 + co) * 8 + (ci & 7)]), acc);
+      t[co] = __bfloat162float(__float2bfloat16(fmaxf(acc + bias[co], 0.f)));
+    }
+    for (int co = 0; co < 32; ++co) h[co] = t[co];
+  }
+  const size_t N3 = (size_t)S * S * S;
+  for (int co = 0; co < p.cout_real; ++co) {
+    float acc = 0.f;
+    for (int ci = 0; ci < 32; ++ci) acc = fmaf(h[ci], __bfloat162float(p.w3[((size_t)(ci >> 3) * 16 + co) * 8 + (ci & 7)]), acc);
+    p.dst[((size_t)b * p.cout_real + co) * N3 + n] = acc + p.b3[co];
+  }
+}
+
+// Called by sceneego_v2v_run for SCENEEGO_OP_TAIL_MLP.  Blob segment at op.w_offset:
+// [w1 2048 B][w2 2048 B][w3 1024 B][b1 32 f32][b2 32 f32][b3 16 f32].
+int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
+                    bool simt, cudaStream_t st) {
+  SE_REQUIRE(op.cin == 32 && op.cout == 16 && op.cout_real >= 1 && op.cout_real <= 16 && (op.flags & SCENEEGO_F_OUT_F32),
+             "v2v_run: op %d: the fused tail is 32 -> 32 -> 32 -> (<=16) with f32 output", op_index);
+  SE_REQUIRE(op.lay_src.s2d == 0, "v2v_run: op %d: the fused tail reads a plain layout", op_index);
+  TailParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = (const __nv_bfloat16*)d_buffers[op.src];
+  p.dst = (float*)d_buffers[op.dst];
+  SE_REQUIRE(p.src && p.dst, "v2v_run: op %d has a null buffer", op_index);
+  const char* seg = (const char*)d_blob + op.w_offset;
+  p.w1 = (const __nv_bfloat16*)seg;
+  p.w2 = (const __nv_bfloat16*)(seg + 2048);
+  p.w3 = (const __nv_bfloat16*)(seg + 4096);
+  p.b1 = (const float*)(seg + 5120);
+  p.b2 = p.b1 + 32;
+  p.b3 = p.b2 + 32;
+  p.ls = op.lay_src; p.batch = batch; p.cout_real = op.cout_real;
+  p.n_pos = (int64_t)batch * p.ls.frame_pitch;
+  SE_REQUIRE(p.n_pos + 4096 < (1ll << 31) && (p.n_pos + 4096) * (int64_t)p.ls.frame_pitch < (1ll << 48),
+             "v2v_run: op %d: batch * frame_pitch too large for one launch", op_index);
+  p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);
+  p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
+  p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
+  if (simt) {
+    const int S = p.ls.side;
+    dim3 grid((S * S * S + 127) / 128, batch);
+    tail_mlp_simt_kernel<<<grid, 128, 0, st>>>(p);
+    SE_CUDA_LAUNCH_CHECK("tail_mlp_simt");
+    return SCENEEGO_OK;
+  }
+  const int64_t n_chunks = (p.n_pos + 31) / 32;
+  int64_t blocks = (n_chunks + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  tail_mlp_kernel<<<(int)blocks, 256, 0, st>>>(p);
+  SE_CUDA_LAUNCH_CHECK("tail_mlp");
+  return SCENEEGO_OK;
+}
+
+}  // namespace sceneego

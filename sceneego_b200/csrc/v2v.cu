@@ -788,8 +788,10 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
       ++g_launches;
       continue;
     }
-    if (op.type == SCENEEGO_OP_STEM7_S2D) {
-      const int rc = launch_stem_s2d(op, d_buffers, d_blob, batch, i, op.impl == 1 || force_simt, st);
+    if (op.type == SCENEEGO_OP_STEM7_S2D || op.type == SCENEEGO_OP_TAIL_MLP) {
+      const bool simt = op.impl == 1 || force_simt;
+      const int rc = op.type == SCENEEGO_OP_STEM7_S2D ? launch_stem_s2d(op, d_buffers, d_blob, batch, i, simt, st)
+                                                      : launch_tail_mlp(op, d_buffers, d_blob, batch, i, simt, st);
       if (rc != SCENEEGO_OK) return rc;
       ++g_launches;
       continue;

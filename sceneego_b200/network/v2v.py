@@ -146,6 +146,11 @@ class _Program:
 
     def pack(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
              xstack: int = 1) -> Tuple[int, int]:
+        w_out, b_out = self.pack_arrays(conv, bn, cin_pad, cout_pad, xstack)
+        return self._append_blob(w_out), self._append_blob(b_out)
+
+    def pack_arrays(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
+                    xstack: int = 1) -> Tuple[np.ndarray, np.ndarray]:
         transposed = isinstance(conv, nn.ConvTranspose3d)
         w = conv.weight.detach().float().cpu().contiguous().numpy()
         k = w.shape[-1]
@@ -170,7 +175,7 @@ class _Program:
                                                         C.c_double(eps), cout, cin, k, int(transposed), cout_pad,
                                                         cin_pad, int(xstack), fp(w_out), fp(b_out))
         _lib._check(rc, "v2v_pack_conv")
-        return self._append_blob(w_out), self._append_blob(b_out)
+        return w_out, b_out
 
     # -- ops -----------------------------------------------------------------
     def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False,
@@ -220,6 +225,30 @@ class _Program:
         self.flops += fl
         self.meta.append(dict(kind="conv", cin=33, cout=16, k=7, side=op.lay_dst.side, flops=fl))
 
+    def tail_mlp(self, blocks, out_conv: nn.Conv3d, src: int, dst: int):
+        """Two 1x1 conv+BN+ReLU blocks and the 1x1 output conv as one op (SCENEEGO_OP_TAIL_MLP)."""
+        parts_w, parts_b = [], []
+        for conv, bn in [(b.block[0], b.block[1]) for b in blocks] + [(out_conv, None)]:
+            assert conv.kernel_size[0] == 1 and conv.in_channels == 32
+            w, b = self.pack_arrays(conv, bn, 32, _pad16(conv.out_channels))
+            parts_w.append(w.view(np.uint8))
+            parts_b.append(b.view(np.uint8))
+        seg = np.concatenate(parts_w + parts_b)
+        assert seg.size == 2048 + 2048 + 1024 + 4 * (32 + 32 + 16)
+        op = _lib.V2VOp()
+        op.type, op.flags = _lib.OP_TAIL_MLP, _lib.F_OUT_F32
+        op.ksize, op.cin, op.cout, op.cout_real = 1, 32, 16, out_conv.out_channels
+        op.src, op.dst, op.res, op.impl, op.xstack = src, dst, -1, 0, 1
+        op.w_offset = self._append_blob(seg)
+        op.b_offset = op.w_offset + 5120
+        op.lay_src = self.lay_of(src)
+        op.lay_dst = self.lay_of(src)
+        self.ops.append(op)
+        side = op.lay_src.side
+        fl = 2 * (32 * 32 * 2 + 32 * out_conv.out_channels) * side ** 3
+        self.flops += fl
+        self.meta.append(dict(kind="tail", cin=32, cout=out_conv.out_channels, k=1, side=side, flops=fl))
+
     def pool(self, src: int, dst: int, channels: int):
         op = _lib.V2VOp()
         op.type, op.cin, op.cout, op.cout_real = _lib.OP_MAXPOOL2, channels, channels, channels
@@ -262,6 +291,7 @@ class V2VModel(nn.Module):
         self.max_chunk = max_chunk
         self.stem_xstack = 4
         self.c32_xstack = 2      # 3^3 convs with Cout = 32: stack two x-planes (N = 64)
+        self.fuse_tail = True
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
                                           Res3DBlock(32, 32), Res3DBlock(32, 32))
         self.encoder_decoder = EncoderDecorder()
@@ -343,16 +373,20 @@ class V2VModel(nn.Module):
         y = self._res(pg, self.back_layers[0], x, 0)
         pg.release(x)
         x = y
-        for i in (1, 2):
-            y = pg.acquire(0)
-            pg.conv(self.back_layers[i].block[0], self.back_layers[i].block[1], x, y, relu=True)
-            pg.release(x)
-            x = y
-        # output layer writes f32 logits (B,J,V,V,V); its dst buffer slot is patched per call
+        # f32 logits (B,J,V,V,V): the dst buffer slot is patched per call
         pg.buffers.append(torch.empty(0, device=device))
         pg.buf_level.append(0)
         pg.logits_buf = len(pg.buffers) - 1
-        pg.conv(self.output_layer, None, x, pg.logits_buf, relu=False, out_f32=True)
+        if self.fuse_tail and self.output_channels <= 16:
+            # the three trailing 1x1 convs are HBM-bound: one fused pass (csrc/tail.cu)
+            pg.tail_mlp([self.back_layers[1], self.back_layers[2]], self.output_layer, x, pg.logits_buf)
+        else:
+            for i in (1, 2):
+                y = pg.acquire(0)
+                pg.conv(self.back_layers[i].block[0], self.back_layers[i].block[1], x, y, relu=True)
+                pg.release(x)
+                x = y
+            pg.conv(self.output_layer, None, x, pg.logits_buf, relu=False, out_f32=True)
         pg.finalize()
         return pg
 

@@ -20,13 +20,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list out of sync with the header"
-    assert lib.sceneego_abi_version() == 1
+    assert lib.sceneego_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Calib) == 8 * 20 + 8          # 20 doubles + 2 int32
-    assert ctypes.sizeof(_lib.VolLayout) == 32
-    assert ctypes.sizeof(_lib.V2VOp) == 12 * 4 + 16 + 2 * 32      # 11 int32 + pad, 2 int64, 2 layouts
+    assert ctypes.sizeof(_lib.VolLayout) == 40               # 6 int32, int64, s2d + reserved
+    assert ctypes.sizeof(_lib.V2VOp) == 12 * 4 + 16 + 2 * 40      # 11 int32 + pad, 2 int64, 2 layouts
 
 
 def test_host_only_entry_points():
@@ -35,7 +35,11 @@ def test_host_only_entry_points():
     assert lay.guard >= 4225 + 65 + 1 and lay.guard % 8 == 0 and lay.frame_pitch % 8 == 0
     assert lay.plane_stride >= 4 * lay.frame_pitch + lay.guard + 1024
     lay7 = _lib.vol_layout(64, 3, 1)
-    assert lay7.guard >= 3 * (67 * 67 + 67 + 1)
+    assert lay7.guard >= 3 * (67 * 67 + 67 + 1) and lay7.s2d == 0
+    s2d = _lib.vol_layout_s2d(64, 2)                          # stem input: 8 parity sub-volumes of side 32, pad 2
+    assert (s2d.s2d, s2d.side, s2d.pad, s2d.pitch_y, s2d.pitch_x) == (1, 32, 2, 34, 34 * 34)
+    assert s2d.guard >= 2 * s2d.pitch_x + 2 * (s2d.pitch_y + 1)
+    assert _lib.load_library().sceneego_v2v_stem_s2d_weight_bytes() == 276 * 16384
 
 
 def test_missing_library_fails_loudly(tmp_path):

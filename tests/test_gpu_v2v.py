@@ -210,3 +210,24 @@ def test_v2v_simt_and_tc_whole_network_agree():
     m.run_chunk(pg, 2, a, impl=0)   # again: buffers reused, pads must still be clean
     torch.cuda.synchronize()
     assert ((a - b).norm() / b.norm()).item() <= 2e-2   # accumulation order x 52 bf16-rounded layers
+
+
+def test_fused_tail_matches_unfused_chain():
+    """SCENEEGO_OP_TAIL_MLP (three 1x1 convs in registers, csrc/tail.cu) vs the same layers run one by one:
+    identical bf16 roundings, only the fp32 summation order differs."""
+    from sceneego_b200.network.v2v import V2VModel
+    from sceneego_b200.utils import synth
+    m = V2VModel(33, 15).eval()
+    sd = synth.synthetic_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=4, mode="random_bn")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x = torch.randn(2, 33, 32, 32, 32, generator=torch.Generator().manual_seed(9)).abs().cuda()
+    with torch.no_grad():
+        fused = m(x)
+        m.fuse_tail = False
+        m.invalidate()
+        plain = m(x)
+    assert [op.type for op in m.program(32, 2, x.device).ops].count(4) == 0
+    scale = plain.abs().max().item()
+    assert (fused - plain).abs().max().item() <= 8e-3 * scale      # one bf16 ulp of the hidden activations, propagated
+    assert ((fused - plain).norm() / plain.norm()).item() <= 2e-3

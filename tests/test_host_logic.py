@@ -31,7 +31,7 @@ def test_program_structure_and_flops():
     assert abs(V2VModel(32, 15).flops_per_frame(64) / 1e9 - 296.2) < 0.1
     pg = m.program(32, 2, torch.device("cpu"))
     kinds = [op.type for op in pg.ops]
-    assert kinds.count(_lib.OP_CONV) == 46 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
+    assert kinds.count(_lib.OP_CONV) == 43 and kinds.count(_lib.OP_TAIL_MLP) == 1 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
     assert kinds[0] == _lib.OP_STEM7_S2D
     assert pg.flops * 8 == m.flops_per_frame(64)
     assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 33 and pg.ops[0].cout == 16
@@ -39,7 +39,7 @@ def test_program_structure_and_flops():
     pg32 = V2VModel(32, 15).program(32, 1, torch.device("cpu"))          # no occupancy channel: plain x-stacked stem
     assert pg32.ops[0].type == _lib.OP_CONV and pg32.ops[0].cin == 32 and pg32.ops[0].lay_src.pad == 3
     last = pg.ops[-1]
-    assert last.flags & _lib.F_OUT_F32 and last.cout_real == 15 and last.cout == 16
+    assert last.type == _lib.OP_TAIL_MLP and last.flags & _lib.F_OUT_F32 and last.cout_real == 15 and last.cout == 16
     # every op reads a buffer some earlier op (or the input staging) wrote, and never its own output
     written = {pg.in_buf}
     for op in pg.ops:
