@@ -189,6 +189,8 @@ typedef struct sceneego_v2v_op {
   int32_t impl;        /* 0 = tcgen05 implicit GEMM, 1 = CUDA-core checker kernel          */
   int32_t xstack;      /* conv: GEMM rows produce `xstack` consecutive x-planes (N = xstack*cout),
                           weights packed with the same xstack; 0/1 = off                    */
+  int32_t cta_pair;    /* conv: 2 = run on CTA pairs (tcgen05 cta_group::2, M = 256); weights packed
+                          with n_split = 2; 0/1 = one CTA per tile                          */
   int64_t w_offset;    /* byte offset of the packed bf16 weights in the blob               */
   int64_t b_offset;    /* byte offset of the fp32 bias (cout entries) in the blob          */
   sceneego_vol_layout_t lay_src, lay_dst;
@@ -198,20 +200,23 @@ typedef struct sceneego_v2v_op {
  *   h_weight: Conv3d (cout,cin,k,k,k) fp32, or ConvTranspose3d (cin,cout,2,2,2) if transposed
  *   bn_*: NULL for no BatchNorm.  Output: bf16 [tap][cin_pad/8][cout_pad][8] and fp32 bias.
  *   xstack > 1: Toeplitz-stacked for x-stacking, [(k+xstack-1)*k*k][cin_pad/8][xstack*cout_pad][8]:
- *   column block s of input-plane offset dxp holds W[dx = dxp - s] (zero where out of range). */
+ *   column block s of input-plane offset dxp holds W[dx = dxp - s] (zero where out of range).
+ *   n_split = 2 (CTA pairs): the N columns are split in two halves, each a complete blob of its own,
+ *   [half][tap][cin_pad/8][N/2][8] -- the B operand of tcgen05.mma.cta_group::2 is N-split over the pair. */
 int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
                            const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
                            double eps, int cout, int cin, int ksize, int transposed, int cout_pad,
-                           int cin_pad, int xstack, uint16_t* h_w_out, float* h_b_out);
+                           int cin_pad, int xstack, int n_split, uint16_t* h_w_out, float* h_b_out);
 
 /* Same for the 7^3 stem read from a space-to-depth source (SCENEEGO_OP_STEM7_S2D):
  *   h_weight (16,33,7,7,7) fp32.  Output: sceneego_v2v_stem_s2d_weight_bytes() bytes of bf16 in the
  *   kernel's streaming order (2x2x2 output-stacked Toeplitz blocks per input offset, the occupancy
- *   channel packed along K) and 16 fp32 biases. */
+ *   channel packed along K) and 16 fp32 biases.  n_split = 2 packs the 128 stacked columns as two
+ *   half-major blobs for CTA pairs (op.cta_pair = 2). */
 size_t sceneego_v2v_stem_s2d_weight_bytes(void);
 int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
                                const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
-                               double eps, uint16_t* h_w_out, float* h_b_out);
+                               double eps, int n_split, uint16_t* h_w_out, float* h_b_out);
 
 /* Execute `n_ops` steps on `batch` frames.  d_blob: packed weights + biases. */
 int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,

@@ -48,10 +48,13 @@ struct StemParams {
   int batch, relu, n_items;
   int halo, win_cells;        // halo = 2 * (pitch_y + 1); window = L + 2 * halo + 8 cells
   int win_stages, w_slots;
+  int cg;                     // 2: CTA pairs (tcgen05 cta_group::2), weights N-split: blob = [half][chunk][tap][kchunk][64][8]
+  uint32_t chunk_bytes;       // weight chunk bytes staged per CTA: 16 KB / cg
   uint32_t win_bytes, off_w, off_bias, off_bar;
   FastDiv fd_frame, fd_px, fd_py;
 };
 
+template <int CG>
 __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -66,24 +69,41 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
                 B_TMEM_EMPTY = B_TMEM_FULL + 1, B_COUNT = B_TMEM_EMPTY + 1;
   uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
+  // CTA pair (CG = 2): rank 0 issues every MMA (M = 256 = one tile of each CTA); see conv_tc_kernel
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   if (threadIdx.x < 16) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STEM_MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), 1); mbar_init(BAR(B_EMPTY_WIN + i), STEM_TILES); }
-    for (int i = 0; i < STEM_MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), 1); mbar_init(BAR(B_EMPTY_W + i), STEM_TILES); }
+    const int full_cnt = (CG == 2 && is_leader) ? 2 : 1;       // own TMA + the peer's relayed arrival
+    for (int i = 0; i < STEM_MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), full_cnt); mbar_init(BAR(B_EMPTY_WIN + i), STEM_TILES); }
+    for (int i = 0; i < STEM_MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), full_cnt); mbar_init(BAR(B_EMPTY_W + i), STEM_TILES); }
     mbar_init(BAR(B_TMEM_FULL), STEM_TILES);
-    mbar_init(BAR(B_TMEM_EMPTY), 8);
+    mbar_init(BAR(B_TMEM_EMPTY), 8 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
-  const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_cl = (int)gridDim.x / CG, cl = (int)blockIdx.x / CG;
+  const int n_groups = (p.n_items + CG - 1) / CG;
+  const int my_items = (n_groups - cl + n_cl - 1) / n_cl;
+  auto item_of = [&](int it) -> int {
+    const int item = (cl + it * n_cl) * CG + (int)cta_rank;
+    return item < p.n_items ? item : p.n_items - 1;          // odd item count: the peer repeats the last item
+  };
   const int pitch_y = p.ls.pitch_y, pitch_x = p.ls.pitch_x;
   const uint32_t stage_bytes = 4u * p.win_bytes;
 
@@ -92,7 +112,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
     if (lane == 0) {
       int ws = 0, wph = 0, sl = 0, sph = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * STEM_L;
+        const int64_t q0 = (int64_t)p.ls.guard + (int64_t)item_of(it) * STEM_L;
         int chunk = 0;
         for (int s = 0; s < STEM_FEAT_STAGES + STEM_SCENE_STAGES; ++s) {
           const bool feat = s < STEM_FEAT_STAGES;
@@ -114,9 +134,9 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
           if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
           for (int c = 0; c < n_chunks; ++c, ++chunk) {
             mbar_wait(BAR(B_EMPTY_W + sl), sph ^ 1);
-            mbar_expect_tx(BAR(B_FULL_W + sl), STEM_CHUNK_BYTES);
-            bulk_g2s(sbase + p.off_w + (uint32_t)sl * STEM_CHUNK_BYTES, p.w + (size_t)chunk * STEM_CHUNK_BYTES,
-                     STEM_CHUNK_BYTES, BAR(B_FULL_W + sl));
+            mbar_expect_tx(BAR(B_FULL_W + sl), p.chunk_bytes);
+            bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.chunk_bytes,
+                     p.w + ((size_t)cta_rank * STEM_N_CHUNKS + (size_t)chunk) * p.chunk_bytes, p.chunk_bytes, BAR(B_FULL_W + sl));
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
@@ -124,31 +144,59 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
     }
   } else if (warp <= STEM_TILES) {
     // ===================== MMA issuers: warp w owns tile w-1 (TMEM columns 128*(w-1)..+127) ===========
+    if (CG == 2 && !is_leader) {
+      // peer CTA: warp 1 relays "landed" to the leader's full barriers in consumption order
+      if (warp == 1 && lane == 0) {
+        int ws = 0, wph = 0, sl = 0, sph = 0;
+        for (int it = 0; it < my_items; ++it)
+          for (int s = 0; s < STEM_FEAT_STAGES + STEM_SCENE_STAGES; ++s) {
+            mbar_wait(BAR(B_FULL_WIN + ws), wph);
+            mbar_arrive_remote(mapa_shared(BAR(B_FULL_WIN + ws), 0));
+            if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+            const int n_chunks = s < STEM_FEAT_STAGES ? STEM_FEAT_CHUNKS : STEM_SCENE_CHUNKS;
+            for (int c = 0; c < n_chunks; ++c) {
+              mbar_wait(BAR(B_FULL_W + sl), sph);
+              mbar_arrive_remote(mapa_shared(BAR(B_FULL_W + sl), 0));
+              if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+            }
+          }
+      }
+    } else {
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (8u << 24);
+    auto WAIT = [&](uint32_t bar, uint32_t parity) {
+      if constexpr (CG == 2) mbar_wait_warp_cluster(bar, parity); else mbar_wait_warp(bar, parity);
+    };
+    auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t ac) {
+      if constexpr (CG == 2) tc_mma_bf16_pair(d, a, b, id, ac); else tc_mma_bf16(d, a, b, id, ac);
+    };
+    auto COMMIT = [&](uint32_t bar) {
+      if constexpr (CG == 2) tc_commit_pair(bar); else tc_commit(bar);
+    };
+    constexpr uint32_t NH = 128 / CG;                                      // B rows (columns of D) staged per CTA
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((CG == 2 ? 16u : 8u) << 24);
     const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;            // SBO = 128 B, descriptor version 1
     const uint32_t a_lbo_feat = ((uint32_t)p.win_cells & 0x3FFFu) << 16;   // K chunk 1 = next channel-group plane
     const uint32_t a_lbo_scene = 1u << 16;                                 // K chunk 1 = next block in z (16 B)
-    const uint32_t b_lbo = (128u & 0x3FFFu) << 16;                         // [kchunk][128 columns][8]: 2 KB apart
+    const uint32_t b_lbo = (NH & 0x3FFFu) << 16;                           // [kchunk][NH columns][8]: NH * 16 B apart
     const uint32_t my_tile = (uint32_t)(warp - 1);
     const uint32_t d_mine = tmem_u + my_tile * 128u;
     const uint32_t a_ks = 2u * (uint32_t)p.win_cells;                      // K step = two planes
     int ws = 0, wph = 0, sl = 0, sph = 0;
     for (int it = 0; it < my_items; ++it) {
-      mbar_wait_warp(BAR(B_TMEM_EMPTY), (it & 1) ^ 1);
+      WAIT(BAR(B_TMEM_EMPTY), (it & 1) ^ 1);
       tc_fence_after();
       uint32_t acc = 0;
       for (int s = 0; s < STEM_FEAT_STAGES + STEM_SCENE_STAGES; ++s) {
-        mbar_wait_warp(BAR(B_FULL_WIN + ws), wph);
+        WAIT(BAR(B_FULL_WIN + ws), wph);
         // first cell of this tile's rows at block shift (.., 0, 0)
         const uint32_t a_org = ((sbase + (uint32_t)ws * stage_bytes) >> 4) + (uint32_t)p.halo + my_tile * 128u;
         if (s < STEM_FEAT_STAGES) {
           const int py = (s >> 1) & 1, pz = s & 1;
           for (int c = 0; c < STEM_FEAT_CHUNKS; ++c) {
-            mbar_wait_warp(BAR(B_FULL_W + sl), sph);
+            WAIT(BAR(B_FULL_W + sl), sph);
             tc_fence_after();
-            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * STEM_CHUNK_BYTES) >> 4) & 0x3FFFu) | b_lbo;
+            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * p.chunk_bytes) >> 4) & 0x3FFFu) | b_lbo;
             const int by = (c >> 1) - 1 - py;
             const int bz0 = (c & 1) * 2 - 1 - pz;
             const uint32_t a_row = a_org + (uint32_t)(by * pitch_y + bz0);
@@ -157,46 +205,47 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
               for (int j = 0; j < 2; ++j) {
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
-                  tc_mma_bf16(d_mine, desc_hi | (((a_row + (uint32_t)j + (uint32_t)ks * a_ks) & 0x3FFFu) | a_lbo_feat),
-                              desc_hi | (b_org + (uint32_t)(j * 512 + ks * 256)), idesc, (j == 0 && ks == 0) ? acc : 1u);
+                  MMA(d_mine, desc_hi | (((a_row + (uint32_t)j + (uint32_t)ks * a_ks) & 0x3FFFu) | a_lbo_feat),
+                      desc_hi | (b_org + (uint32_t)(j * 4 + ks * 2) * NH), idesc, (j == 0 && ks == 0) ? acc : 1u);
               }
             }
             acc = 1;
-            if (leader) tc_commit(BAR(B_EMPTY_W + sl));
+            if (leader) COMMIT(BAR(B_EMPTY_W + sl));
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         } else {
           for (int c = 0; c < STEM_SCENE_CHUNKS; ++c) {
-            mbar_wait_warp(BAR(B_FULL_W + sl), sph);
+            WAIT(BAR(B_FULL_W + sl), sph);
             tc_fence_after();
-            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * STEM_CHUNK_BYTES) >> 4) & 0x3FFFu) | b_lbo;
+            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * p.chunk_bytes) >> 4) & 0x3FFFu) | b_lbo;
             if (leader) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int tp = c * 4 + j;                 // 0..14: (by, bz pair); 15: zero-weight filler
                 const int by = tp < 15 ? tp / 3 - 2 : 0;
                 const int bz0 = tp < 15 ? (tp % 3) * 2 - 2 : 0;
-                tc_mma_bf16(d_mine, desc_hi | (((a_org + (uint32_t)(by * pitch_y + bz0)) & 0x3FFFu) | a_lbo_scene),
-                            desc_hi | (b_org + (uint32_t)(j * 256)), idesc, 1u);
+                MMA(d_mine, desc_hi | (((a_org + (uint32_t)(by * pitch_y + bz0)) & 0x3FFFu) | a_lbo_scene),
+                    desc_hi | (b_org + (uint32_t)(j * 2) * NH), idesc, 1u);
               }
             }
-            if (leader) tc_commit(BAR(B_EMPTY_W + sl));
+            if (leader) COMMIT(BAR(B_EMPTY_W + sl));
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
-        if (leader) tc_commit(BAR(B_EMPTY_WIN + ws));
+        if (leader) COMMIT(BAR(B_EMPTY_WIN + ws));
         if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
       }
-      if (leader) tc_commit(BAR(B_TMEM_FULL));
+      if (leader) COMMIT(BAR(B_TMEM_FULL));
     }
     __syncwarp();
+    }
   } else {
     // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
     const int quarter = warp & 3;
     const int half = (warp - (1 + STEM_TILES)) >> 2;
     const int S2 = p.ls.side;
     for (int it = 0; it < my_items; ++it) {
-      const int64_t q0 = (int64_t)p.ls.guard + (int64_t)(blockIdx.x + it * gridDim.x) * STEM_L;
+      const int64_t q0 = (int64_t)p.ls.guard + (int64_t)item_of(it) * STEM_L;
       mbar_wait(BAR(B_TMEM_FULL), it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -239,13 +288,20 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_TMEM_EMPTY));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_remote(mapa_shared(BAR(B_TMEM_EMPTY), 0));
+        else mbar_arrive(BAR(B_TMEM_EMPTY));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -266,20 +322,22 @@ __global__ void __launch_bounds__(128) stem_s2d_simt_kernel(const __grid_constan
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   const uint4* wq = reinterpret_cast<const uint4*>(p.w);
+  const int nh = 128 / p.cg, hf = col0 / nh, colh = col0 - hf * nh;   // CTA-pair blobs are half-major
+  const size_t half_u4 = (size_t)STEM_N_CHUNKS * p.chunk_bytes / 16;
   for (int s = 0; s < STEM_FEAT_STAGES; ++s) {
     const int ox = (s >> 2) - 3, py = (s >> 1) & 1, pz = s & 1;
     const int bx = ox >> 1, plane0 = (((ox & 1) << 2) | (s & 3)) * 4;
     for (int tp = 0; tp < 16; ++tp) {
       const int by = (tp >> 2) - 1 - py, bz = (tp & 3) - 1 - pz;
       const int64_t qs = q + (int64_t)bx * p.ls.pitch_x + (int64_t)by * p.ls.pitch_y + bz;
-      const uint4* wt = wq + ((size_t)(s * STEM_FEAT_CHUNKS) * STEM_CHUNK_BYTES + (size_t)tp * 8192) / 16;   // [kchunk 4][128][8]
+      const uint4* wt = wq + (size_t)hf * half_u4 + ((size_t)(s * STEM_FEAT_CHUNKS) * p.chunk_bytes + (size_t)tp * (8192 / p.cg)) / 16;   // [kchunk 4][nh][8]
       for (int g = 0; g < 4; ++g) {
         float a[8];
         unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)(plane0 + g) * p.ls.plane_stride + qs) * 8), a);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float wv[8];
-          unpack8(__ldg(wt + g * 128 + col0 + j), wv);
+          unpack8(__ldg(wt + g * nh + colh + j), wv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], wv[i], acc[j]);
         }
@@ -290,8 +348,8 @@ __global__ void __launch_bounds__(128) stem_s2d_simt_kernel(const __grid_constan
     const int bx = s - 2;
     for (int tp = 0; tp < 15; ++tp) {
       const int by = tp / 3 - 2, bz0 = (tp % 3) * 2 - 2;
-      const uint4* wt = wq + ((size_t)(STEM_FEAT_STAGES * STEM_FEAT_CHUNKS + s * STEM_SCENE_CHUNKS) * STEM_CHUNK_BYTES +
-                              (size_t)tp * 4096) / 16;                                                       // [kchunk 2][128][8]
+      const uint4* wt = wq + (size_t)hf * half_u4 + ((size_t)(STEM_FEAT_STAGES * STEM_FEAT_CHUNKS + s * STEM_SCENE_CHUNKS) * p.chunk_bytes +
+                              (size_t)tp * (4096 / p.cg)) / 16;                                              // [kchunk 2][nh][8]
       for (int c2 = 0; c2 < 2; ++c2) {
         const int64_t qs = q + (int64_t)bx * p.ls.pitch_x + (int64_t)by * p.ls.pitch_y + bz0 + c2;
         float a[8];
@@ -299,7 +357,7 @@ __global__ void __launch_bounds__(128) stem_s2d_simt_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float wv[8];
-          unpack8(__ldg(wt + c2 * 128 + col0 + j), wv);
+          unpack8(__ldg(wt + c2 * nh + colh + j), wv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], wv[i], acc[j]);
         }
@@ -332,6 +390,8 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   p.w = (const uint8_t*)d_blob + op.w_offset;
   p.bias = (const float*)((const char*)d_blob + op.b_offset);
   p.ls = op.lay_src; p.ld = op.lay_dst; p.batch = batch; p.relu = (op.flags & SCENEEGO_F_RELU) ? 1 : 0;
+  p.cg = op.cta_pair == 2 ? 2 : 1;
+  p.chunk_bytes = STEM_CHUNK_BYTES / p.cg;
   SE_REQUIRE(p.src && p.dst, "v2v_run: op %d has a null buffer", op_index);
   if (simt) {
     const int V = p.ld.side;
@@ -354,25 +414,40 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   int stages = STEM_MAX_STAGES, slots = 0;
   for (; stages >= 2; --stages) {
     const uint32_t used = 4u * p.win_bytes * stages + fixed;
-    if (used + 3u * STEM_CHUNK_BYTES > kMaxSmem) continue;
-    slots = (int)((kMaxSmem - used) / STEM_CHUNK_BYTES);
+    if (used + 3u * p.chunk_bytes > kMaxSmem) continue;
+    slots = (int)((kMaxSmem - used) / p.chunk_bytes);
     if (slots > STEM_MAX_WSLOTS) slots = STEM_MAX_WSLOTS;
     break;
   }
   SE_REQUIRE(stages >= 2 && slots >= 3, "v2v_run: op %d: stem windows do not fit shared memory (side %d)", op_index, p.ld.side);
   p.win_stages = stages; p.w_slots = slots;
   p.off_w = 4u * p.win_bytes * stages;
-  p.off_bias = p.off_w + (uint32_t)slots * STEM_CHUNK_BYTES;
+  p.off_bias = p.off_w + (uint32_t)slots * p.chunk_bytes;
   p.off_bar = p.off_bias + 128;
   p.n_items = (int)((n_pos + STEM_L - 1) / STEM_L);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_s2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(stem_s2d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_s2d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
     configured = true;
   }
-  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  stem_s2d_tc_kernel<<<grid, STEM_THREADS, kMaxSmem, st>>>(p);
+  if (p.cg == 2) {
+    const int groups = (p.n_items + 1) / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * (groups < kNumSMs / 2 ? groups : kNumSMs / 2))); cfg.blockDim = dim3(STEM_THREADS);
+    cfg.dynamicSmemBytes = kMaxSmem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, stem_s2d_tc_kernel<2>, p);
+    if (e != cudaSuccess) { set_error("stem_s2d_tc (CTA pair): %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+  } else {
+    const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+    stem_s2d_tc_kernel<1><<<grid, STEM_THREADS, kMaxSmem, st>>>(p);
+  }
   SE_CUDA_LAUNCH_CHECK("stem_s2d_tc");
   return SCENEEGO_OK;
 }
@@ -385,8 +460,10 @@ extern "C" size_t sceneego_v2v_stem_s2d_weight_bytes(void) { return (size_t)STEM
 
 extern "C" int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_bias, const float* h_gamma,
                                           const float* h_beta, const float* h_mean, const float* h_var, double eps,
-                                          uint16_t* h_w_out, float* h_b_out) {
-  SE_REQUIRE(h_weight && h_w_out && h_b_out, "pack_stem_s2d: null argument");
+                                          int n_split, uint16_t* h_w_out, float* h_b_out) {
+  SE_REQUIRE(h_weight && h_w_out && h_b_out && (n_split == 1 || n_split == 2), "pack_stem_s2d: bad argument");
+  const int NHp = 128 / n_split;                                    // columns per half-blob
+  const size_t half_elems = (size_t)STEM_N_CHUNKS * STEM_CHUNK_BYTES / 2 / n_split;
   constexpr int CO = 16, CI = 33, K = 7;
   memset(h_w_out, 0, (size_t)STEM_N_CHUNKS * STEM_CHUNK_BYTES);
   double scale[CO];
@@ -409,11 +486,13 @@ extern "C" int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_
     for (int tp = 0; tp < 16; ++tp) {
       const int by = (tp >> 2) - 1 - py, bz = (tp & 3) - 1 - pz;
       const int oy = 2 * by + py, oz = 2 * bz + pz;
-      uint16_t* dst = h_w_out + ((size_t)(s * STEM_FEAT_CHUNKS) * STEM_CHUNK_BYTES + (size_t)tp * 8192) / 2;
+      // within a half-blob: chunk stride 16 KB / n_split, tap stride 8 KB / n_split, [kchunk 4][NHp][8]
+      uint16_t* dst = h_w_out + ((size_t)(s * STEM_FEAT_CHUNKS) * STEM_CHUNK_BYTES + (size_t)tp * 8192) / 2 / n_split;
       for (int n = 0; n < 128; ++n) {
         const int sx = n >> 6, sy = (n >> 5) & 1, sz = (n >> 4) & 1, co = n & 15;
+        const int hf = n / NHp, nn = n % NHp;
         for (int ci = 0; ci < 32; ++ci)
-          dst[((size_t)(ci >> 3) * 128 + n) * 8 + (ci & 7)] = W(co, ci, ox - sx + 3, oy - sy + 3, oz - sz + 3);
+          dst[hf * half_elems + ((size_t)(ci >> 3) * NHp + nn) * 8 + (ci & 7)] = W(co, ci, ox - sx + 3, oy - sy + 3, oz - sz + 3);
       }
     }
   }
@@ -423,13 +502,14 @@ extern "C" int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_
     for (int tp = 0; tp < 15; ++tp) {
       const int by = tp / 3 - 2, bz0 = (tp % 3) * 2 - 2;
       uint16_t* dst = h_w_out + ((size_t)(STEM_FEAT_STAGES * STEM_FEAT_CHUNKS + s * STEM_SCENE_CHUNKS) * STEM_CHUNK_BYTES +
-                                 (size_t)tp * 4096) / 2;
+                                 (size_t)tp * 4096) / 2 / n_split;
       for (int c2 = 0; c2 < 2; ++c2)
         for (int n = 0; n < 128; ++n) {
           const int sx = n >> 6, sy = (n >> 5) & 1, sz = (n >> 4) & 1, co = n & 15;
+          const int hf = n / NHp, nn = n % NHp;
           for (int e = 0; e < 8; ++e) {
             const int ox = 2 * bx + (e >> 2), oy = 2 * by + ((e >> 1) & 1), oz = 2 * (bz0 + c2) + (e & 1);
-            dst[((size_t)c2 * 128 + n) * 8 + e] = W(co, 32, ox - sx + 3, oy - sy + 3, oz - sz + 3);
+            dst[hf * half_elems + ((size_t)c2 * NHp + nn) * 8 + e] = W(co, 32, ox - sx + 3, oy - sy + 3, oz - sz + 3);
           }
         }
     }

@@ -62,6 +62,12 @@ struct ConvParams {
   uint32_t off_win, off_w, off_bias, off_bar;
   uint32_t tmem_cols, half_cols;
   int debug;                        // SCENEEGO_DEBUG bit mask (tuning experiments only; 0 in production)
+  // CTA pair (cg = 2): two CTAs of one cluster run one tcgen05.mma.cta_group::2 stream (M = 256 = one
+  // 128-row tile of each CTA) issued by the leader; each CTA stages its own windows and HALF of the
+  // weight columns (B is N-split across the pair), which halves the weight traffic and the B-operand
+  // shared-memory reads that bound N <= 128 MMAs.  Weights are packed half-major: [half][tap][cin/8][N/2][8].
+  int cg;
+  uint32_t w_half_bytes;            // bytes of one half-blob (cg = 2)
 };
 
 constexpr int CONV_EPI_WARPS = 8;
@@ -196,7 +202,7 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const RowInfo& 
 // descriptors differ by constants: the single issuing lane must sustain one tcgen05.mma per
 // ~41 cycles (measured floor at N<=32, tools/mma_rate.cu).
 // ---------------------------------------------------------------------------
-template <int KSTEPS, int TILES, int XS, int WROWS>
+template <int KSTEPS, int TILES, int XS, int WROWS, int CG>
 __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are
@@ -216,24 +222,45 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
   constexpr int NW = conv_mma_warps(TILES);          // MMA-issuing warps: warps 1..NW
   constexpr int FIRST_EPI = 1 + NW;                  // epilogue warps: FIRST_EPI .. FIRST_EPI+7
   for (int i = threadIdx.x; i < p.n0; i += conv_threads(TILES)) s_bias[i] = p.bias[i];
+  // CTA pair: rank 0 (leader) issues every MMA for both CTAs; its "full" barriers also count one arrival
+  // relayed from the peer (the peer's data has landed), its accumulator-empty barrier counts both epilogues.
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), 1); mbar_init(BAR(B_EMPTY_WIN + i), NW); }
-    for (int i = 0; i < MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), 1); mbar_init(BAR(B_EMPTY_W + i), NW); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), NW); mbar_init(BAR(B_TMEM_EMPTY + i), CONV_EPI_WARPS); }
+    const int full_cnt = (CG == 2 && is_leader) ? 2 : 1;
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(BAR(B_FULL_WIN + i), full_cnt); mbar_init(BAR(B_EMPTY_WIN + i), NW); }
+    for (int i = 0; i < MAX_WSLOTS; ++i) { mbar_init(BAR(B_FULL_W + i), full_cnt); mbar_init(BAR(B_EMPTY_W + i), NW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TMEM_FULL + i), NW); mbar_init(BAR(B_TMEM_EMPTY + i), CONV_EPI_WARPS * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)),
-                 "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_ptr)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
 
-  const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work split: cluster c of n_cl clusters takes item groups c, c + n_cl, ...; CTA r of the pair takes item
+  // CG * group + r (the last group of an odd item count repeats the last item: same values written twice)
+  const int n_cl = (int)gridDim.x / CG, cl = (int)blockIdx.x / CG;
+  const int n_groups = (p.n_items + CG - 1) / CG;
+  const int my_items = (n_groups - cl + n_cl - 1) / n_cl;
+  auto item_of = [&](int it) -> int {
+    const int item = (cl + it * n_cl) * CG + (int)cta_rank;
+    return item < p.n_items ? item : p.n_items - 1;
+  };
   const int halo = p.r * (p.ls.pitch_y + 1);   // window starts `halo` positions before the item
   constexpr int L = TILES * 128;
   // first position of work item `item`; for x-stacked items also frame / first plane / first cell
@@ -253,7 +280,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
       int n_win_issued = 0, n_w_issued = 0;
       for (int it = 0; it < my_items; ++it) {
         int ib, ix0, icell0;
-        const int64_t q0 = item_origin(blockIdx.x + it * gridDim.x, ib, ix0, icell0);
+        const int64_t q0 = item_origin(item_of(it), ib, ix0, icell0);
         for (int dx = 0; dx < p.n_dx; ++dx) {
           mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
           if ((p.debug & 4) && n_win_issued >= p.win_stages) { mbar_arrive(BAR(B_FULL_WIN + ws)); }
@@ -273,7 +300,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
             else {
             ++n_w_issued;
             mbar_expect_tx(BAR(B_FULL_W + sl), p.wchunk_bytes);
-            const char* wsrc = reinterpret_cast<const char*>(p.w) +
+            const char* wsrc = reinterpret_cast<const char*>(p.w) + (size_t)cta_rank * p.w_half_bytes +
                                (size_t)(dx * p.wchunks_per_dx + wc) * p.wchunk_bytes;
             bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes, wsrc, p.wchunk_bytes, BAR(B_FULL_W + sl));
             }
@@ -289,18 +316,46 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
     // The whole warp runs this loop converged so that every descriptor is a warp-uniform value
     // (uniform registers, no per-MMA R2UR/ELECT loop); only the tcgen05 instructions themselves
     // are predicated on one elected lane, which is also the lane that commits.
+    if (CG == 2 && !is_leader) {
+      // peer CTA of a pair: no MMAs of its own.  Warp 1 relays "my window / weight half has landed" to the
+      // leader's full barriers, in consumption order; warps 2..NW have nothing to do.
+      if (warp == 1 && lane == 0) {
+        int ws = 0, wph = 0, sl = 0, sph = 0;
+        for (int it = 0; it < my_items; ++it)
+          for (int dx = 0; dx < p.n_dx; ++dx) {
+            mbar_wait(BAR(B_FULL_WIN + ws), wph);
+            mbar_arrive_remote(mapa_shared(BAR(B_FULL_WIN + ws), 0));
+            if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+            for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
+              mbar_wait(BAR(B_FULL_W + sl), sph);
+              mbar_arrive_remote(mapa_shared(BAR(B_FULL_W + sl), 0));
+              if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+            }
+          }
+      }
+    } else {
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = elect_one();
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=p.N
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.mma_n >> 3) << 17) | (8u << 24);
+    auto WAIT = [&](uint32_t bar, uint32_t parity) {
+      if constexpr (CG == 2) mbar_wait_warp_cluster(bar, parity); else mbar_wait_warp(bar, parity);
+    };
+    auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t ac) {
+      if constexpr (CG == 2) tc_mma_bf16_pair(d, a, b, id, ac); else tc_mma_bf16(d, a, b, id, ac);
+    };
+    auto COMMIT = [&](uint32_t bar) {
+      if constexpr (CG == 2) tc_commit_pair(bar); else tc_commit(bar);
+    };
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128 (256 over a CTA pair), N=p.mma_n
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.mma_n >> 3) << 17) | ((CG == 2 ? 16u : 8u) << 24);
     // K-major no-swizzle: LBO = byte stride between the two 8-channel K chunks of one MMA,
     // SBO = byte stride between 8-row core matrices (validated on B200 hardware).
     // hi word: SBO = 128 B (>>4 = 8) | descriptor version 1 (bit 46 -> bit 14 of the hi word)
     const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
     const uint32_t a_lo_flags = ((p.win_bytes >> 4) & 0x3FFFu) << 16;          // LBO = window plane stride
-    const uint32_t b_lo_flags = (((uint32_t)p.mma_n * 16u >> 4) & 0x3FFFu) << 16;  // LBO = N * 16 B
+    const uint32_t n_mine = (uint32_t)p.mma_n / CG;                            // B rows staged in this CTA (N-split over a pair)
+    const uint32_t b_lo_flags = ((n_mine * 16u >> 4) & 0x3FFFu) << 16;         // LBO = rows * 16 B
     const uint32_t a_ks_step = (2u * p.win_bytes) >> 4;                        // two planes per K step
-    const uint32_t b_ks_step = (2u * (uint32_t)p.mma_n * 16u) >> 4;
+    const uint32_t b_ks_step = (2u * n_mine * 16u) >> 4;
     const uint32_t b_tap_step = p.tap_bytes >> 4;
     const uint32_t n_cols = (uint32_t)p.N;
     const int pitch_y = p.ls.pitch_y, ksz = p.k, wtaps = p.wchunk_taps;
@@ -310,18 +365,18 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
     int ws = 0, wph = 0, sl = 0, sph = 0;
     for (int it = 0; it < my_items; ++it) {
       const int buf = it & 1;
-      mbar_wait_warp(BAR(B_TMEM_EMPTY + buf), ((it >> 1) & 1) ^ 1);
+      WAIT(BAR(B_TMEM_EMPTY + buf), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_mine = tmem_u + (uint32_t)buf * p.half_cols + my_tile * n_cols;
       uint32_t acc = 0;
       for (int dx = 0; dx < p.n_dx; ++dx) {
-        mbar_wait_warp(BAR(B_FULL_WIN + ws), wph);
+        WAIT(BAR(B_FULL_WIN + ws), wph);
         const uint32_t win_lo = (((sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS) * p.win_bytes) >> 4) & 0x3FFFu) |
                                 a_lo_flags;
         int dy = 0, dz = 0;
         uint32_t dcol = 0;                                                     // deconv: parity column block
         for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
-          mbar_wait_warp(BAR(B_FULL_W + sl), sph);
+          WAIT(BAR(B_FULL_W + sl), sph);
           tc_fence_after();
           uint32_t b_lo = (((sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes) >> 4) & 0x3FFFu) | b_lo_flags;
           if constexpr (WROWS == 0) {
@@ -333,7 +388,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
                 for (int tt = 0; tt < TILES / NW; ++tt) {
 #pragma unroll
                   for (int ks = 0; ks < KSTEPS; ++ks)
-                    tc_mma_bf16(d_mine + (uint32_t)(tt * NW) * n_cols + dcol,
+                    MMA(d_mine + (uint32_t)(tt * NW) * n_cols + dcol,
                                 desc_hi | (a_lo + a_mine + (uint32_t)(tt * NW) * 128u + (uint32_t)ks * a_ks_step),
                                 desc_hi | (b_lo + (uint32_t)ks * b_ks_step), idesc, ks == 0 ? acc : 1u);
                 }
@@ -355,7 +410,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
                   for (int tt = 0; tt < TILES / NW; ++tt) {
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks)
-                      tc_mma_bf16(d_mine + (uint32_t)(tt * NW) * n_cols,
+                      MMA(d_mine + (uint32_t)(tt * NW) * n_cols,
                                   desc_hi | (a_row + (uint32_t)j + (uint32_t)(tt * NW) * 128u + (uint32_t)ks * a_ks_step),
                                   desc_hi | (b_lo + (uint32_t)(r * 3 + j) * b_tap_step + (uint32_t)ks * b_ks_step), idesc,
                                   (ks == 0 && r == 0 && j == 0) ? acc : 1u);
@@ -366,15 +421,16 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
             acc = 1;
             dy += WROWS;
           }
-          if (leader) tc_commit(BAR(B_EMPTY_W + sl));
+          if (leader) COMMIT(BAR(B_EMPTY_W + sl));
           if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
         }
-        if (leader) tc_commit(BAR(B_EMPTY_WIN + ws));
+        if (leader) COMMIT(BAR(B_EMPTY_WIN + ws));
         if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
       }
-      if (leader) tc_commit(BAR(B_TMEM_FULL + buf));
+      if (leader) COMMIT(BAR(B_TMEM_FULL + buf));
     }
     __syncwarp();
+    }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     // Chunks of 16 output channels; the residual cells of chunk i+1 are requested before chunk i
@@ -413,7 +469,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
     for (int it = 0; it < my_items; ++it) {
       const int buf = it & 1;
       int ib, ix0, icell0;
-      const int64_t q0 = item_origin(blockIdx.x + it * gridDim.x, ib, ix0, icell0);
+      const int64_t q0 = item_origin(item_of(it), ib, ix0, icell0);
       auto row_info = [&](int t) -> RowInfo {
         const int r = t * 128 + quarter * 32 + lane;
         return XS == 1 ? decode_row(p, q0 + r) : decode_row_plane(p, ib, ix0, icell0 + r);
@@ -451,28 +507,47 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_TMEM_EMPTY + buf));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_remote(mapa_shared(BAR(B_TMEM_EMPTY + buf), 0));   // the leader issues for both
+        else mbar_arrive(BAR(B_TMEM_EMPTY + buf));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();        // both CTAs are done with the pair's tensor memory
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
 typedef void (*conv_tc_fn)(const ConvParams);
+// CTA-pair instantiations: the full-resolution 3^3 layers with N = 64 (where the B operand's shared-memory
+// read is a quarter of the MMA's operand traffic) and the 64-channel layers at half resolution.
+static conv_tc_fn pick_conv_tc_pair(int ksteps, int tiles, int xs, int wrows) {
+  if (xs == 2 && ksteps == 2 && tiles == 4 && wrows == 3) return conv_tc_kernel<2, 4, 2, 3, 2>;
+  if (xs == 2 && ksteps == 2 && tiles == 4 && wrows == 1) return conv_tc_kernel<2, 4, 2, 1, 2>;
+  if (xs == 2 && ksteps == 1 && tiles == 4 && wrows == 3) return conv_tc_kernel<1, 4, 2, 3, 2>;
+  if (xs == 1 && ksteps == 4 && tiles == 4 && wrows == 3) return conv_tc_kernel<4, 4, 1, 3, 2>;
+  if (xs == 1 && ksteps == 4 && tiles == 4 && wrows == 1) return conv_tc_kernel<4, 4, 1, 1, 2>;
+  if (xs == 1 && ksteps == 2 && tiles == 4 && wrows == 3) return conv_tc_kernel<2, 4, 1, 3, 2>;
+  if (xs == 1 && ksteps == 2 && tiles == 4 && wrows == 0) return conv_tc_kernel<2, 4, 1, 0, 2>;
+  return nullptr;
+}
 template <int WROWS>
 static conv_tc_fn pick_conv_tc_w(int ksteps, int tiles, int xs) {
-  if (xs == 4 && ksteps == 3 && tiles == 4) return conv_tc_kernel<3, 4, 4, WROWS>;
-  if (xs == 4 && ksteps == 3 && tiles == 2) return conv_tc_kernel<3, 2, 4, WROWS>;
-  if (xs == 4 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 4, WROWS>;
-  if (xs == 4 && ksteps == 2 && tiles == 2) return conv_tc_kernel<2, 2, 4, WROWS>;
-  if (xs == 2 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 2, WROWS>;
-  if (xs == 2 && ksteps == 1 && tiles == 4) return conv_tc_kernel<1, 4, 2, WROWS>;
-  if (xs == 2 && ksteps == 4 && tiles == 2) return conv_tc_kernel<4, 2, 2, WROWS>;
+  if (xs == 4 && ksteps == 3 && tiles == 4) return conv_tc_kernel<3, 4, 4, WROWS, 1>;
+  if (xs == 4 && ksteps == 3 && tiles == 2) return conv_tc_kernel<3, 2, 4, WROWS, 1>;
+  if (xs == 4 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 4, WROWS, 1>;
+  if (xs == 4 && ksteps == 2 && tiles == 2) return conv_tc_kernel<2, 2, 4, WROWS, 1>;
+  if (xs == 2 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 2, WROWS, 1>;
+  if (xs == 2 && ksteps == 1 && tiles == 4) return conv_tc_kernel<1, 4, 2, WROWS, 1>;
+  if (xs == 2 && ksteps == 4 && tiles == 2) return conv_tc_kernel<4, 2, 2, WROWS, 1>;
   if (xs != 1) return nullptr;
-#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T, 1, WROWS>;
+#define SE_CASE(K, T) if (ksteps == K && tiles == T) return conv_tc_kernel<K, T, 1, WROWS, 1>;
   SE_CASE(2, 4) SE_CASE(4, 4) SE_CASE(4, 2) SE_CASE(8, 2) SE_CASE(1, 4) SE_CASE(1, 2) SE_CASE(2, 2)
   SE_CASE(8, 1) SE_CASE(4, 1) SE_CASE(2, 1) SE_CASE(1, 1) SE_CASE(1, 8) SE_CASE(2, 8)
   if (WROWS == 0) {
@@ -513,7 +588,10 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
           for (int g = 0; g < p.cin_planes; ++g) {
             float a[8];
             unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8), a);
-            const uint4* wrow = reinterpret_cast<const uint4*>(p.w) + ((size_t)tap * p.cin_planes + g) * p.N + c0;  // p.N = xs*n0
+            // p.N = xs*n0 columns; CTA-pair blobs are packed half-major ([half][tap][cin/8][N/2][8])
+            const int nh = p.cg == 2 ? p.N / 2 : p.N, hf = c0 / nh;
+            const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.w) + (size_t)hf * p.w_half_bytes) +
+                                ((size_t)tap * p.cin_planes + g) * nh + (c0 - hf * nh);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float wv[8];
@@ -653,7 +731,7 @@ static bool try_plan(ConvParams& p, int tiles, int want_stages) {
 }
 
 static int plan_conv(ConvParams& p) {
-  p.tap_bytes = (uint32_t)p.cin_planes * p.mma_n * 16u;   // mma_n includes the x-stacking factor
+  p.tap_bytes = (uint32_t)p.cin_planes * (p.mma_n / p.cg) * 16u;   // per CTA; mma_n includes the x-stacking factor
   int max_tiles = 256 / p.N;
   if (max_tiles > 8) max_tiles = 8;
   const char* et = getenv("SCENEEGO_TILES");
@@ -664,10 +742,13 @@ static int plan_conv(ConvParams& p) {
     if (tiles >= 1 && tiles <= max_tiles && stages >= 1 && stages <= MAX_STAGES && try_plan(p, tiles, stages))
       return (int)(p.off_bar + 512);
   }
-  // measured on B200 (tools/tune_conv.py): the largest item with a 2-stage window ring wins for every
-  // 3^3 / 7^3 layer; 1x1 convs have no halo, so their small windows get a deeper ring
+  // measured on B200 (tools/tune_conv.py, tools/pair_sweep.py): the largest item wins; a 2-stage window ring is
+  // enough for the single-CTA 3^3 / 7^3 layers, but CTA pairs (the peer's "landed" signal is relayed through
+  // the leader: one more hop of latency) and the 16-channel input layer (short stages) want 3; 1x1 convs have
+  // no halo, so their small windows get a deeper ring
+  const int first_stages = p.k == 1 ? 4 : (p.cg == 2 || p.cin_planes <= 2) ? 3 : 2;
   for (int tiles = max_tiles; tiles >= 1; tiles >>= 1)
-    for (int stages = (p.k == 1 ? 4 : 2); stages >= 2; --stages)
+    for (int stages = first_stages; stages >= 2; --stages)
       if (try_plan(p, tiles, stages)) return (int)(p.off_bar + 512);
   return -1;
 }
@@ -683,10 +764,11 @@ extern "C" int sceneego_v2v_last_launch_count(void) { return g_launches; }
 extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const float* h_gamma,
                                       const float* h_beta, const float* h_mean, const float* h_var, double eps,
                                       int cout, int cin, int ksize, int transposed, int cout_pad, int cin_pad,
-                                      int xstack, uint16_t* h_w_out, float* h_b_out) {
+                                      int xstack, int n_split, uint16_t* h_w_out, float* h_b_out) {
   SE_REQUIRE(h_weight && h_w_out && h_b_out, "pack_conv: null argument");
   SE_REQUIRE(cout_pad >= cout && cin_pad >= cin && cout_pad % 8 == 0 && cin_pad % 8 == 0, "pack_conv: bad padding");
   SE_REQUIRE(xstack >= 1 && (xstack == 1 || !transposed), "pack_conv: bad xstack");
+  SE_REQUIRE(n_split == 1 || (n_split == 2 && !transposed && (xstack * cout_pad) % 32 == 0), "pack_conv: bad n_split");
   const int taps = ksize * ksize * ksize;
   const int kk = ksize * ksize;
   const int n_stk = xstack * cout_pad;                 // columns of the stacked B operand
@@ -713,7 +795,10 @@ extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias
         const int dx = t / kk, rest = t % kk;
         for (int sft = 0; sft < xstack; ++sft) {
           const size_t tp = (size_t)(dx + sft) * kk + rest;
-          const size_t dst = ((tp * (cin_pad / 8) + ci / 8) * n_stk + (size_t)sft * cout_pad + co) * 8 + (ci & 7);
+          const size_t col = (size_t)sft * cout_pad + co;
+          const size_t nh = (size_t)n_stk / n_split, hf = col / nh;               // n_split = 2: half-major blob
+          const size_t half_elems = (size_t)n_dx * kk * cin_pad * nh;
+          const size_t dst = hf * half_elems + ((tp * (cin_pad / 8) + ci / 8) * nh + (col - hf * nh)) * 8 + (ci & 7);
           h_w_out[dst] = wv;
         }
       }
@@ -739,11 +824,19 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
     p.n_xg = (p.ls.side + p.xs - 1) / p.xs;
     p.n_items = batch * p.n_xg * p.items_per_plane;
   }
-  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  conv_tc_fn fn = pick_conv_tc(p.ksteps, p.tiles, p.xs, p.wrows);
-  if (fn == nullptr && p.wrows != 0) { p.wrows = 0; fn = pick_conv_tc(p.ksteps, p.tiles, p.xs, 0); }   // same chunking, generic tap loop
-  SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d xs=%d wrows=%d", op_index, p.ksteps,
-             p.tiles, p.xs, p.wrows);
+  int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  conv_tc_fn fn = nullptr;
+  if (p.cg == 2) {
+    p.w_half_bytes = (uint32_t)(p.n_dx * p.taps_dx) * p.tap_bytes;
+    const int groups = (p.n_items + 1) / 2;
+    grid = 2 * (groups < kNumSMs / 2 ? groups : kNumSMs / 2);
+    fn = pick_conv_tc_pair(p.ksteps, p.tiles, p.xs, p.wrows);
+  } else {
+    fn = pick_conv_tc(p.ksteps, p.tiles, p.xs, p.wrows);
+    if (fn == nullptr && p.wrows != 0) { p.wrows = 0; fn = pick_conv_tc(p.ksteps, p.tiles, p.xs, 0); }   // same chunking, generic tap loop
+  }
+  SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d xs=%d wrows=%d cta_pair=%d", op_index,
+             p.ksteps, p.tiles, p.xs, p.wrows, p.cg);
   {
     static conv_tc_fn configured[96];
     static int n_configured = 0;
@@ -755,7 +848,20 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
       if (n_configured < 96) configured[n_configured++] = fn;
     }
   }
-  fn<<<grid, conv_threads(p.tiles), kMaxSmem, st>>>(p);
+  if (p.cg == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)conv_threads(p.tiles));
+    cfg.dynamicSmemBytes = kMaxSmem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
+    if (e != cudaSuccess) { set_error("conv_tc (CTA pair): %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+  } else {
+    fn<<<grid, conv_threads(p.tiles), kMaxSmem, st>>>(p);
+  }
   SE_CUDA_LAUNCH_CHECK("conv_tc");
   ++g_launches;
   return SCENEEGO_OK;
@@ -799,7 +905,7 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
     p.w = (const __nv_bfloat16*)((const char*)d_blob + op.w_offset);
     p.bias = (const float*)((const char*)d_blob + op.b_offset);
     p.cin_planes = op.cin / 8; p.ksteps = op.cin / 16; p.N = op.cout; p.cout_real = op.cout_real;
-    p.xs = 1; p.n0 = op.cout; p.n_dx = op.ksize; p.n_xg = 0; p.items_per_plane = 0;
+    p.xs = 1; p.n0 = op.cout; p.n_dx = op.ksize; p.n_xg = 0; p.items_per_plane = 0; p.cg = 1;
     if (op.type == SCENEEGO_OP_DECONV2) {
       SE_REQUIRE(op.lay_dst.side == 2 * op.lay_src.side && op.cin % 8 == 0 && op.cout % 8 == 0, "v2v_run: op %d bad deconv shape", i);
       if (op.impl == 1 || force_simt || op.cin % 16 || op.cout % 16 || op.cout > 256) {
@@ -834,8 +940,10 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
     p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);      // the checker kernel decodes rows too
     p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
     p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
+    p.cg = op.cta_pair == 2 ? 2 : 1;
     if (op.impl == 1 || force_simt) {
       p.n0 = op.cout; p.N = (op.xstack > 1 ? op.xstack : 1) * op.cout;   // weight row stride of the stacked blob
+      p.w_half_bytes = (uint32_t)((op.ksize + (op.xstack > 1 ? op.xstack : 1) - 1) * op.ksize * op.ksize) * p.cin_planes * (p.N / 2) * 16u;
       dim3 grid((unsigned)((n_pos + 127) / 128), op.cout / 16);
       conv_simt_kernel<<<grid, 128, 0, st>>>(p, n_pos);
       SE_CUDA_LAUNCH_CHECK("conv_simt");
@@ -844,6 +952,7 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
     }
     const int xs = op.xstack > 1 ? op.xstack : 1;
     SE_REQUIRE(xs * op.cout <= 256, "v2v_run: op %d: xstack * cout exceeds 256 columns", i);
+    SE_REQUIRE(p.cg == 1 || (xs * op.cout) % 32 == 0, "v2v_run: op %d: a CTA pair splits N in halves of whole 16-column groups", i);
     p.xs = xs; p.n0 = op.cout; p.N = xs * op.cout; p.mma_n = p.N; p.n_dx = op.ksize + xs - 1;
     p.deconv = 0; p.par0 = 0; p.taps_dx = op.ksize * op.ksize;
     const int rc = launch_conv_tc(p, batch, i, st);

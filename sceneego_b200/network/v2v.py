@@ -145,12 +145,12 @@ class _Program:
         return off
 
     def pack(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
-             xstack: int = 1) -> Tuple[int, int]:
-        w_out, b_out = self.pack_arrays(conv, bn, cin_pad, cout_pad, xstack)
+             xstack: int = 1, n_split: int = 1) -> Tuple[int, int]:
+        w_out, b_out = self.pack_arrays(conv, bn, cin_pad, cout_pad, xstack, n_split)
         return self._append_blob(w_out), self._append_blob(b_out)
 
     def pack_arrays(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
-                    xstack: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+                    xstack: int = 1, n_split: int = 1) -> Tuple[np.ndarray, np.ndarray]:
         transposed = isinstance(conv, nn.ConvTranspose3d)
         w = conv.weight.detach().float().cpu().contiguous().numpy()
         k = w.shape[-1]
@@ -173,21 +173,21 @@ class _Program:
             eps = 0.0
         rc = _lib.load_library().sceneego_v2v_pack_conv(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var),
                                                         C.c_double(eps), cout, cin, k, int(transposed), cout_pad,
-                                                        cin_pad, int(xstack), fp(w_out), fp(b_out))
+                                                        cin_pad, int(xstack), int(n_split), fp(w_out), fp(b_out))
         _lib._check(rc, "v2v_pack_conv")
         return w_out, b_out
 
     # -- ops -----------------------------------------------------------------
     def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False,
-             xstack: int = 1):
+             xstack: int = 1, cta_pair: int = 1):
         k = conv.kernel_size[0]
         cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
-        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad, xstack)
+        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad, xstack, cta_pair)
         op = _lib.V2VOp()
         op.type = _lib.OP_CONV
         op.flags = (_lib.F_RELU if relu else 0) | (_lib.F_RESIDUAL if res >= 0 else 0) | (_lib.F_OUT_F32 if out_f32 else 0)
         op.ksize, op.cin, op.cout, op.cout_real = k, cin_pad, cout_pad, conv.out_channels
-        op.src, op.dst, op.res, op.impl, op.xstack = src, dst, res, 0, xstack
+        op.src, op.dst, op.res, op.impl, op.xstack, op.cta_pair = src, dst, res, 0, xstack, cta_pair
         op.w_offset, op.b_offset = w_off, b_off
         op.lay_src = self.lay_of(src)
         op.lay_dst = self.lay_of(dst) if not out_f32 else self.lay_of(src)
@@ -197,7 +197,7 @@ class _Program:
         self.meta.append(dict(kind="conv", cin=conv.in_channels, cout=conv.out_channels, k=k,
                               side=op.lay_src.side, flops=fl))
 
-    def stem_s2d(self, conv: nn.Conv3d, bn, src: int, dst: int):
+    def stem_s2d(self, conv: nn.Conv3d, bn, src: int, dst: int, cta_pair: int = 1):
         """7^3 stem from the space-to-depth input (SCENEEGO_OP_STEM7_S2D)."""
         lib = _lib.load_library()
         assert conv.in_channels == 33 and conv.out_channels == 16 and conv.kernel_size[0] == 7
@@ -213,11 +213,11 @@ class _Program:
         mu = bn.running_mean.detach().float().cpu().contiguous().numpy()
         var = bn.running_var.detach().float().cpu().contiguous().numpy()
         _lib._check(lib.sceneego_v2v_pack_stem_s2d(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var), C.c_double(float(bn.eps)),
-                                                   fp(w_out), fp(b_out)), "v2v_pack_stem_s2d")
+                                                   int(cta_pair), fp(w_out), fp(b_out)), "v2v_pack_stem_s2d")
         op = _lib.V2VOp()
         op.type, op.flags = _lib.OP_STEM7_S2D, _lib.F_RELU
         op.ksize, op.cin, op.cout, op.cout_real = 7, 33, 16, 16
-        op.src, op.dst, op.res, op.impl, op.xstack = src, dst, -1, 0, 1
+        op.src, op.dst, op.res, op.impl, op.xstack, op.cta_pair = src, dst, -1, 0, 1, cta_pair
         op.w_offset, op.b_offset = self._append_blob(w_out), self._append_blob(b_out)
         op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
         self.ops.append(op)
@@ -292,6 +292,7 @@ class V2VModel(nn.Module):
         self.stem_xstack = 4
         self.c32_xstack = 2      # 3^3 convs with Cout = 32: stack two x-planes (N = 64)
         self.fuse_tail = True
+        self.cta_pair = 2        # 1 = every conv on single CTAs
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
                                           Res3DBlock(32, 32), Res3DBlock(32, 32))
         self.encoder_decoder = EncoderDecorder()
@@ -319,15 +320,17 @@ class V2VModel(nn.Module):
 
     def _res(self, pg: _Program, blk: Res3DBlock, x: int, level: int) -> int:
         xs = self.c32_xstack if blk.res_branch[0].out_channels == 32 else 1
+        # CTA pairs (tcgen05 cta_group::2) where the B operand's shared-memory read bounds the MMA: N = 64
+        cg = self.cta_pair if (xs * blk.res_branch[0].out_channels == 64 and level <= 1 and blk.res_branch[0].in_channels >= 32) else 1
         t = pg.acquire(level)
-        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs)
+        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs, cta_pair=cg)
         if len(blk.skip_con) > 0:
             s = pg.acquire(level)
             pg.conv(blk.skip_con[0], blk.skip_con[1], x, s, relu=False)
         else:
             s = x
         y = pg.acquire(level)
-        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s, xstack=xs)
+        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s, xstack=xs, cta_pair=cg)
         pg.release(t)
         if s != x:
             pg.release(s)
@@ -342,7 +345,7 @@ class V2VModel(nn.Module):
         # 7^3 stem, Cout = 16: the worst tcgen05 shape (N = 16 costs as much as N = 32 per MMA), so four
         # adjacent x-planes of outputs are stacked into N = 64 (tools/mma_rate.cu for the cost model)
         if pg.s2d:
-            pg.stem_s2d(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x)
+            pg.stem_s2d(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, cta_pair=self.cta_pair)
         else:
             pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True,
                     xstack=self.stem_xstack)

@@ -63,6 +63,12 @@ def _voxelize(cam, depth, V, side=2.0):
     _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, side, occ, buf, lay, channel=32)
     planar = _lib.unpack_volume(buf, lay, d.shape[0], 40)[:, 32]
     assert torch.equal(planar, occ), "planar bf16 scene channel differs from the f32 grid"
+    # the stem's space-to-depth input: the 2x2x2 block's occupancy bits share one 16-byte cell
+    lay2 = _lib.vol_layout_s2d(V, d.shape[0])
+    buf2 = _lib.alloc_volume(lay2, 33 * 8, "cuda")
+    _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, side, None, buf2, lay2, channel=32)
+    assert torch.equal(_lib.unpack_volume(buf2, lay2, d.shape[0], 33)[:, 32], occ), "s2d scene channel differs"
+    assert buf2[:32].abs().max().item() == 0.0, "s2d voxelisation touched a feature plane"
     return occ.cpu().numpy()
 
 
@@ -153,6 +159,14 @@ def test_unproject_vs_reference_golden(cam, tables64):
         planar = _lib.unpack_volume(buf, lay, 2, 48)
         assert torch.equal(planar[:, :32], out.to(torch.bfloat16).float())   # same values, bf16-rounded
         assert planar[:, 32:].abs().max().item() == 0.0
+        # same gather written in the stem's space-to-depth layout; the occupancy plane is cleared
+        lay2 = _lib.vol_layout_s2d(64, 2)
+        buf2 = _lib.alloc_volume(lay2, 33 * 8, "cuda")
+        buf2[32].fill_(1.0)
+        _lib.unproject(feat32, grid, cam.calib_struct(1280, 1024) if fused else None, 64, 2.0, 1024, 1280, None, buf2,
+                       lay2, extra_zero_planes=1)
+        s2d = _lib.unpack_volume(buf2, lay2, 2, 33)
+        assert torch.equal(s2d[:, :32], planar[:, :32]) and s2d[:, 32].abs().max().item() == 0.0
 
 
 def test_materialised_features_and_generic_grid_sample(tables64):

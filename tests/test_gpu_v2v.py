@@ -111,8 +111,34 @@ def test_x_stacked_conv(cin, cout, k, S, B, pad_src, xs):
     assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
 
 
+@pytest.mark.parametrize("cin,cout,k,S,B,xs", [(32, 32, 3, 16, 3, 2), (32, 32, 3, 64, 1, 2), (16, 32, 3, 16, 2, 2),
+                                                (64, 64, 3, 16, 5, 1), (32, 64, 3, 8, 3, 1)])
+def test_cta_pair_conv(cin, cout, k, S, B, xs):
+    """tcgen05 cta_group::2: M = 256 over two CTAs of a cluster, weights N-split across the pair.
+    Same math as the single-CTA kernel on the same inputs (odd item counts repeat the last item)."""
+    conv, bn = _mk_conv(cin, cout, k, seed=17 + xs)
+    g = torch.Generator().manual_seed(S * 3 + B)
+    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    res = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
+    got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, xstack=xs, cta_pair=2)
+    _close(got, _ref(x, conv, bn, True, res=res), f"cta pair conv {cin}->{cout} k{k} S{S}")
+    one, _, _ = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, xstack=xs, cta_pair=1)
+    assert ((got - one).abs() <= 0.0079 * one.abs() + 1e-4).all()
+    simt, _, _ = util.run_single_op(x, conv, bn, relu=True, res=res, impl=1, xstack=xs, cta_pair=2)
+    assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()        # checker reads the half-major blob
+    plane = dst[0].float()
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(S, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
+
+
+@pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("V,B", [(16, 2), (32, 3), (64, 1)])
-def test_stem_s2d(V, B):
+def test_stem_s2d(V, B, pair):
     """7^3 stem from the space-to-depth input: 2x2x2 output stacking, occupancy packed along K."""
     from sceneego_b200 import _lib
     conv, bn = _mk_conv(33, 16, 7, seed=5)
@@ -120,10 +146,10 @@ def test_stem_s2d(V, B):
     x = util.bf16_round(torch.randn(B, 33, V, V, V, generator=g))
     x[:, 32] = (x[:, 32] > 0.8).float()                       # occupancy channel is {0,1}
     x = x.cuda()
-    got, dst, lay, src, lay_s = util.run_stem_s2d(x, conv, bn, impl=0)
+    got, dst, lay, src, lay_s = util.run_stem_s2d(x, conv, bn, impl=0, cta_pair=pair)
     assert torch.equal(_lib.unpack_volume(src, lay_s, B, 33), x)          # s2d pack/unpack round trip (bf16-exact input)
     _close(got, _ref(x, conv, bn, True), f"stem s2d V{V}")
-    simt, _, _, _, _ = util.run_stem_s2d(x, conv, bn, impl=1)
+    simt, _, _, _, _ = util.run_stem_s2d(x, conv, bn, impl=1, cta_pair=pair)
     assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()      # same blob, other summation order
     plane = dst[0].float()
     mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)

@@ -73,7 +73,7 @@ def test_pack_conv_folds_batchnorm():
         bp = np.zeros(cout_p, np.float32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         assert lib.sceneego_v2v_pack_conv(p(w), p(b), p(gamma), p(beta), p(mean), p(var), C.c_double(1e-5), cout, cin,
-                                          k, tr, cout_p, cin_p, 1, p(wp), p(bp)) == 0
+                                          k, tr, cout_p, cin_p, 1, 1, p(wp), p(bp)) == 0
         scale = gamma.astype(np.float64) / np.sqrt(var.astype(np.float64) + 1e-5)
         wf = (w.transpose(1, 0, 2, 3, 4) if tr else w).reshape(cout, cin, taps) * scale[:, None, None]
         got = _unpack(wp, taps, cin_p, cout_p)
@@ -86,8 +86,19 @@ def test_pack_conv_folds_batchnorm():
     w = rng.standard_normal((15, 32, 1, 1, 1)).astype(np.float32)
     wp, bp = np.zeros(32 * 16, np.uint16), np.zeros(16, np.float32)
     assert lib.sceneego_v2v_pack_conv(w.ctypes.data_as(C.c_void_p), None, None, None, None, None, C.c_double(0), 15, 32,
-                                      1, 0, 16, 32, 1, wp.ctypes.data_as(C.c_void_p), bp.ctypes.data_as(C.c_void_p)) == 0
+                                      1, 0, 16, 32, 1, 1, wp.ctypes.data_as(C.c_void_p), bp.ctypes.data_as(C.c_void_p)) == 0
     assert np.all(bp == 0)
+    # CTA-pair blob (n_split = 2): x-stacked columns split in two half-major blobs, same values
+    w = rng.standard_normal((32, 32, 3, 3, 3)).astype(np.float32)
+    taps_s = 4 * 9                                               # xstack 2: (3 + 1) input plane offsets x 9
+    one, two = np.zeros(taps_s * 32 * 64, np.uint16), np.zeros(taps_s * 32 * 64, np.uint16)
+    bp = np.zeros(32, np.float32)
+    for ns, out in ((1, one), (2, two)):
+        assert lib.sceneego_v2v_pack_conv(w.ctypes.data_as(C.c_void_p), None, None, None, None, None, C.c_double(0), 32, 32,
+                                          3, 0, 32, 32, 2, ns, out.ctypes.data_as(C.c_void_p), bp.ctypes.data_as(C.c_void_p)) == 0
+    a = one.reshape(taps_s, 4, 64, 8)
+    b2 = two.reshape(2, taps_s, 4, 32, 8)
+    assert np.array_equal(a[:, :, :32], b2[0]) and np.array_equal(a[:, :, 32:], b2[1])
 
 
 def test_shard_range_partitions_exactly():
@@ -125,7 +136,7 @@ def test_stem_s2d_packing_reproduces_conv3d():
     arrs = [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
     keep = [a.detach().float().contiguous().numpy() for a in arrs]
     ptrs = [k.ctypes.data_as(C.c_void_p) for k in keep]
-    assert lib.sceneego_v2v_pack_stem_s2d(*ptrs, C.c_double(bn.eps), w_out.ctypes.data_as(C.c_void_p),
+    assert lib.sceneego_v2v_pack_stem_s2d(*ptrs, C.c_double(bn.eps), 1, w_out.ctypes.data_as(C.c_void_p),
                                           b_out.ctypes.data_as(C.c_void_p)) == 0
     wf = torch.from_numpy((w_out.astype(np.uint32) << 16).view(np.float32).copy()).double()   # bf16 -> f64
     V, S2, P = 8, 4, 2

@@ -39,7 +39,7 @@ def unpack_bits(packed, V):
     return np.unpackbits(packed)[: V ** 3].reshape(V, V, V).astype(np.float32)
 
 
-def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None, xstack=1):
+def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None, xstack=1, cta_pair=1):
     """Run one V2V op (conv or deconv) through sceneego_v2v_run; x (B,Cin,S,S,S) f32 cuda."""
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program, _pad16
@@ -72,7 +72,7 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     if deconv:
         pg.deconv(conv, bn, 0, 1, add=r_idx)
     else:
-        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack)
+        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack, cta_pair=cta_pair)
     pg.ops[0].impl = impl
     pg.finalize()
     global LAST_PROGRAM
@@ -84,7 +84,7 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     return _lib.unpack_volume(dst, lay_d, B, conv.out_channels), dst, lay_d
 
 
-def run_stem_s2d(x, conv, bn, impl=0):
+def run_stem_s2d(x, conv, bn, impl=0, cta_pair=1):
     """Run the 7^3 stem op (SCENEEGO_OP_STEM7_S2D) on x (B,33,V,V,V) f32 cuda; returns (B,16,V,V,V) f32."""
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program
@@ -102,7 +102,7 @@ def run_stem_s2d(x, conv, bn, impl=0):
     pg.buffers = [src, dst]
     pg.buf_level = [0, 0]
     pg.lay_of = lambda i: lays[i]
-    pg.stem_s2d(conv, bn, 0, 1)
+    pg.stem_s2d(conv, bn, 0, 1, cta_pair=cta_pair)
     pg.ops[0].impl = impl
     pg.finalize()
     global LAST_PROGRAM

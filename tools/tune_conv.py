@@ -17,7 +17,7 @@ def time_layer(cin, cout, k, S, B, pad, xs, tiles, stages, reps=5):
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program, _pad16
     # build once, launch repeatedly
-    got, dst, lay = util.run_single_op(x, conv, bn, relu=True, pad_src=pad, xstack=xs)
+    got, dst, lay = util.run_single_op(x, conv, bn, relu=True, pad_src=pad, xstack=xs, cta_pair=int(os.environ.get('SCENEEGO_TEST_PAIR', '1')))
     pg = util.LAST_PROGRAM
     lib = _lib.load_library()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

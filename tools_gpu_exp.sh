@@ -6,5 +6,6 @@ cut -c 1-300 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 python - <<'PY'
 import json
 ops=json.load(open('gpurun_out/v2v_ops.json'))
-for o in ops[-4:]: print(o)
+for o in ops[:16]: print(o['op'],o['kind'],o['cin'],o['cout'],o['k'],o['side'],round(o['ms_per_frame']*1000,1),round(o.get('tflops') or 0))
+print(sum(o['ms_per_frame'] for o in ops)*1000)
 PY
