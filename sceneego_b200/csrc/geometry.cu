@@ -326,65 +326,68 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
                                                       const double* __restrict__ ray, int img_h, int img_w, int V,
                                                       double side, double inv_side, float* __restrict__ occ_f32,
                                                       __nv_bfloat16* __restrict__ occ_bf16,
-                                                      sceneego_vol_layout_t lay, int channel) {
+                                                      sceneego_vol_layout_t lay, int channel, int batch, int frames_per_block) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y;
-  const int b = blockIdx.z;
   const int pad = (img_w - img_h) / 2;
   const int xs = X - pad;
-  float dv = 0.f;
   const bool in_img = X < img_w;
-  if (in_img && xs >= 0 && xs < img_h) {
-    // cv2.resize(INTER_NEAREST): src = min(floor(dst * in / out), in - 1)
-    int sy = (int)(((long long)Y * h) / img_h);
-    int sx = (int)(((long long)xs * w) / img_h);
-    sy = sy < h - 1 ? sy : h - 1;
-    sx = sx < w - 1 ? sx : w - 1;
-    dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
-  }
-  int ix = -1, iy = 0, iz = 0;
-  const bool zero = in_img && (dv == 0.0f);
-  if (in_img && !zero) {
-    const double d = (double)dv;
+  const bool in_src = in_img && xs >= 0 && xs < img_h;
+  // cv2.resize(INTER_NEAREST): src = min(floor(dst * in / out), in - 1)
+  int sy = (int)(((long long)Y * h) / img_h);
+  int sx = (int)(((long long)(in_src ? xs : 0) * w) / img_h);
+  sy = sy < h - 1 ? sy : h - 1;
+  sx = sx < w - 1 ? sx : w - 1;
+  // the pixel's ray is frame-invariant: fetched once for the `frames_per_block` frames this block covers
+  // (the 31.5 MB table is L2-resident, but at one fetch per frame its L2 traffic, not the depth map, bounds the kernel)
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  if (in_src) {
     const double* r = ray + ((size_t)Y * img_w + X) * 3;
-    const double half = side / 2;             // cuboid_side / 2
-    const double Vd = (double)V;
-    double qx = __dmul_rn(__dadd_rn(__dmul_rn(r[0], d), half), Vd);
-    double qy = __dmul_rn(__dadd_rn(__dmul_rn(r[1], d), half), Vd);
-    double qz = __dmul_rn(__dmul_rn(r[2], d), Vd);
-    if (kPow2Side) {   // x / 2^k == x * 2^-k exactly (no fp64 divide on the hot path)
-      qx = __dmul_rn(qx, inv_side); qy = __dmul_rn(qy, inv_side); qz = __dmul_rn(qz, inv_side);
-    } else {
-      qx = __ddiv_rn(qx, side); qy = __ddiv_rn(qy, side); qz = __ddiv_rn(qz, side);
-    }
-    qx = rint(qx); qy = rint(qy); qz = rint(qz);
-    const double hi = (double)(V - 1);
-    if (qx >= 0.0 && qx <= hi && qy >= 0.0 && qy <= hi && qz >= 0.0 && qz <= hi) {
-      ix = (int)qx; iy = (int)qy; iz = (int)qz;
-    }
+    r0 = r[0]; r1 = r[1]; r2 = r[2];
   }
+  const double half = side / 2;             // cuboid_side / 2
+  const double Vd = (double)V;
+  const double hi = (double)(V - 1);
   // every zero-depth pixel (all the padded columns, everything outside the image circle) lands on
-  // ray*0 -> q = (rint((0+s/2)*V/s), same, 0): one thread per block writes that voxel
-  const int any_zero = __syncthreads_or(zero ? 1 : 0);
-  if (any_zero && threadIdx.x == 0 && ix < 0) {
-    const double half = side / 2, Vd = (double)V;
-    const double q0 = rint(kPow2Side ? __dmul_rn(__dmul_rn(half, Vd), inv_side) : __ddiv_rn(__dmul_rn(half, Vd), side));
-    if (q0 >= 0.0 && q0 <= (double)(V - 1)) { ix = (int)q0; iy = (int)q0; iz = 0; }
-  } else if (any_zero && threadIdx.x == 0) {
-    // thread 0 has its own voxel to write: hand the zero-depth voxel to the write below via a second store
-    const double half = side / 2, Vd = (double)V;
-    const double q0 = rint(kPow2Side ? __dmul_rn(__dmul_rn(half, Vd), inv_side) : __ddiv_rn(__dmul_rn(half, Vd), side));
-    if (q0 >= 0.0 && q0 <= (double)(V - 1)) {
+  // ray*0 -> q = (rint((0+s/2)*V/s), same, 0)
+  const double q0 = rint(kPow2Side ? __dmul_rn(__dmul_rn(half, Vd), inv_side) : __ddiv_rn(__dmul_rn(half, Vd), side));
+  const bool q0_in = q0 >= 0.0 && q0 <= hi;
+  const int b_begin = blockIdx.z * frames_per_block;
+  for (int f = 0; f < frames_per_block; ++f) {
+    const int b = b_begin + f;
+    if (b >= batch) break;                                  // uniform over the block
+    float dv = 0.f;
+    if (in_src) dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
+    int ix = -1, iy = 0, iz = 0;
+    const bool zero = in_img && (dv == 0.0f);
+    if (in_img && !zero) {
+      const double d = (double)dv;
+      double qx = __dmul_rn(__dadd_rn(__dmul_rn(r0, d), half), Vd);
+      double qy = __dmul_rn(__dadd_rn(__dmul_rn(r1, d), half), Vd);
+      double qz = __dmul_rn(__dmul_rn(r2, d), Vd);
+      if (kPow2Side) {   // x / 2^k == x * 2^-k exactly (no fp64 divide on the hot path)
+        qx = __dmul_rn(qx, inv_side); qy = __dmul_rn(qy, inv_side); qz = __dmul_rn(qz, inv_side);
+      } else {
+        qx = __ddiv_rn(qx, side); qy = __ddiv_rn(qy, side); qz = __ddiv_rn(qz, side);
+      }
+      qx = rint(qx); qy = rint(qy); qz = rint(qz);
+      if (qx >= 0.0 && qx <= hi && qy >= 0.0 && qy <= hi && qz >= 0.0 && qz <= hi) {
+        ix = (int)qx; iy = (int)qy; iz = (int)qz;
+      }
+    }
+    // one thread per block writes the zero-depth voxel when any pixel of the block has zero depth
+    const int any_zero = __syncthreads_or(zero ? 1 : 0);
+    if (any_zero && threadIdx.x == 0 && q0_in) {
       const int c = (int)q0;
       if (occ_f32) occ_f32[(((size_t)b * V + c) * V + c) * V] = 1.0f;
       if (occ_bf16)
         occ_bf16[vol_scene_elem(lay, b, c, c, 0, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
     }
-  }
-  if (ix >= 0) {
-    if (occ_f32) occ_f32[(((size_t)b * V + ix) * V + iy) * V + iz] = 1.0f;
-    if (occ_bf16)
-      occ_bf16[vol_scene_elem(lay, b, ix, iy, iz, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
+    if (ix >= 0) {
+      if (occ_f32) occ_f32[(((size_t)b * V + ix) * V + iy) * V + iz] = 1.0f;
+      if (occ_bf16)
+        occ_bf16[vol_scene_elem(lay, b, ix, iy, iz, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
+    }
   }
 }
 
@@ -532,16 +535,18 @@ extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int 
   SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && img_w >= img_h, "voxelize: bad shape");
   SE_REQUIRE(!d_occ_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
   SE_REQUIRE(!d_occ_bf16 || !lay->s2d || channel % 8 == 0, "voxelize: s2d occupancy follows whole channel groups");
-  dim3 grid((img_w + 255) / 256, img_h, batch);
+  // several frames per block so that a pixel's ray is fetched once for all of them (grid.z <= 65535 either way)
+  const int fpb = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
+  dim3 grid((img_w + 255) / 256, img_h, (batch + fpb - 1) / fpb);
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
   int e2 = 0;
   const bool pow2 = side > 0 && frexp(side, &e2) == 0.5;       // side == 2^(e2-1): divide == exact multiply
   if (pow2)
     voxelize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, 1.0 / side,
-                                                                  d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel);
+                                                                  d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb);
   else
     voxelize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, 0.0,
-                                                                   d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel);
+                                                                   d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb);
   SE_CUDA_LAUNCH_CHECK("voxelize");
   return SCENEEGO_OK;
 }

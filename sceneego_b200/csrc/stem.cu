@@ -33,23 +33,26 @@ constexpr int STEM_L = STEM_TILES * 128;
 constexpr int STEM_THREADS = 32 * (1 + STEM_TILES + 8);
 constexpr int STEM_FEAT_STAGES = 32;          // (ox in -3..4) x (py, pz)
 constexpr int STEM_SCENE_STAGES = 5;          // block shift bx in -2..2
-constexpr int STEM_CHUNK_BYTES = 16384;       // weight chunk: 2 feature taps (2 x 8 KB) or 4 scene taps (4 x 4 KB)
-constexpr int STEM_FEAT_CHUNKS = 8;           // 16 taps (4 by x 4 bz) per feature stage
-constexpr int STEM_SCENE_CHUNKS = 4;          // 15 taps (5 by x 3 bz pairs) + 1 zero tap per scene stage
-constexpr int STEM_N_CHUNKS = STEM_FEAT_STAGES * STEM_FEAT_CHUNKS + STEM_SCENE_STAGES * STEM_SCENE_CHUNKS;   // 276
+// Weights stream in 16 KB chunks per CTA.  A feature stage has 16 taps (4 by x 4 bz) of 8 KB, a scene stage
+// 15 taps (5 by x 3 bz pairs) + 1 zero tap of 4 KB.  One CTA: 2 feature / 4 scene taps per chunk; a CTA pair
+// stages half of every tap's columns in each CTA, so its chunks hold twice as many taps (the pair's issue
+// rate is bounded per warp -- tools/mma_pair_rate.cu -- and wants the fewest chunk hand-shakes per MMA).
+constexpr int STEM_CHUNK_BYTES = 16384;
+constexpr int STEM_FEAT_TAP_BYTES = 8192, STEM_SCENE_TAP_BYTES = 4096;
+constexpr size_t STEM_W_BYTES = (size_t)STEM_FEAT_STAGES * 16 * STEM_FEAT_TAP_BYTES + (size_t)STEM_SCENE_STAGES * 16 * STEM_SCENE_TAP_BYTES;   // 4.3 MB
+constexpr size_t STEM_SCENE_OFF = (size_t)STEM_FEAT_STAGES * 16 * STEM_FEAT_TAP_BYTES;
 constexpr int STEM_MAX_STAGES = 3, STEM_MAX_WSLOTS = 8;
 
 struct StemParams {
   const __nv_bfloat16* src;   // 33 planes: plane = parity * 4 + channel group; plane 32 = occupancy blocks
   __nv_bfloat16* dst;         // 16 channels = 2 planes, layout ld
-  const uint8_t* w;           // STEM_N_CHUNKS x 16 KB, streaming order
+  const uint8_t* w;           // STEM_W_BYTES, streaming order (half-major for CTA pairs)
   const float* bias;          // 16
   sceneego_vol_layout_t ls, ld;
   int batch, relu, n_items;
   int halo, win_cells;        // halo = 2 * (pitch_y + 1); window = L + 2 * halo + 8 cells
   int win_stages, w_slots;
   int cg;                     // 2: CTA pairs (tcgen05 cta_group::2), weights N-split: blob = [half][chunk][tap][kchunk][64][8]
-  uint32_t chunk_bytes;       // weight chunk bytes staged per CTA: 16 KB / cg
   uint32_t win_bytes, off_w, off_bias, off_bar;
   FastDiv fd_frame, fd_px, fd_py;
 };
@@ -121,9 +124,9 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
             const int ox = (s >> 2) - 3;
             bx = ox >> 1;                                   // arithmetic shift: floor(ox / 2)
             plane0 = (((ox & 1) << 2) | (s & 3)) * 4;       // parity (px, py, pz) x 4 channel groups
-            n_planes = 4; n_chunks = STEM_FEAT_CHUNKS;
+            n_planes = 4; n_chunks = 16 / (2 * CG);
           } else {
-            bx = s - STEM_FEAT_STAGES - 2; plane0 = 32; n_planes = 1; n_chunks = STEM_SCENE_CHUNKS;
+            bx = s - STEM_FEAT_STAGES - 2; plane0 = 32; n_planes = 1; n_chunks = 16 / (4 * CG);
           }
           mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
           mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * (uint32_t)n_planes);
@@ -134,9 +137,10 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
           if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
           for (int c = 0; c < n_chunks; ++c, ++chunk) {
             mbar_wait(BAR(B_EMPTY_W + sl), sph ^ 1);
-            mbar_expect_tx(BAR(B_FULL_W + sl), p.chunk_bytes);
-            bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.chunk_bytes,
-                     p.w + ((size_t)cta_rank * STEM_N_CHUNKS + (size_t)chunk) * p.chunk_bytes, p.chunk_bytes, BAR(B_FULL_W + sl));
+            mbar_expect_tx(BAR(B_FULL_W + sl), STEM_CHUNK_BYTES);
+            bulk_g2s(sbase + p.off_w + (uint32_t)sl * STEM_CHUNK_BYTES,
+                     p.w + (size_t)cta_rank * (STEM_W_BYTES / CG) + (size_t)chunk * STEM_CHUNK_BYTES, STEM_CHUNK_BYTES,
+                     BAR(B_FULL_W + sl));
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
             mbar_wait(BAR(B_FULL_WIN + ws), wph);
             mbar_arrive_remote(mapa_shared(BAR(B_FULL_WIN + ws), 0));
             if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
-            const int n_chunks = s < STEM_FEAT_STAGES ? STEM_FEAT_CHUNKS : STEM_SCENE_CHUNKS;
+            const int n_chunks = s < STEM_FEAT_STAGES ? 16 / (2 * CG) : 16 / (4 * CG);
             for (int c = 0; c < n_chunks; ++c) {
               mbar_wait(BAR(B_FULL_W + sl), sph);
               mbar_arrive_remote(mapa_shared(BAR(B_FULL_W + sl), 0));
@@ -193,16 +197,18 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
         const uint32_t a_org = ((sbase + (uint32_t)ws * stage_bytes) >> 4) + (uint32_t)p.halo + my_tile * 128u;
         if (s < STEM_FEAT_STAGES) {
           const int py = (s >> 1) & 1, pz = s & 1;
-          for (int c = 0; c < STEM_FEAT_CHUNKS; ++c) {
+          constexpr int TPC = 2 * CG;                     // feature taps per chunk: consecutive in bz, one by
+          for (int c = 0; c < 16 / TPC; ++c) {
             WAIT(BAR(B_FULL_W + sl), sph);
             tc_fence_after();
-            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * p.chunk_bytes) >> 4) & 0x3FFFu) | b_lbo;
-            const int by = (c >> 1) - 1 - py;
-            const int bz0 = (c & 1) * 2 - 1 - pz;
+            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * STEM_CHUNK_BYTES) >> 4) & 0x3FFFu) | b_lbo;
+            const int tp0 = c * TPC;
+            const int by = (tp0 >> 2) - 1 - py;
+            const int bz0 = (tp0 & 3) - 1 - pz;
             const uint32_t a_row = a_org + (uint32_t)(by * pitch_y + bz0);
             if (leader) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
+              for (int j = 0; j < TPC; ++j) {
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
                   MMA(d_mine, desc_hi | (((a_row + (uint32_t)j + (uint32_t)ks * a_ks) & 0x3FFFu) | a_lbo_feat),
@@ -214,14 +220,15 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         } else {
-          for (int c = 0; c < STEM_SCENE_CHUNKS; ++c) {
+          constexpr int TPC = 4 * CG;                     // scene taps per chunk
+          for (int c = 0; c < 16 / TPC; ++c) {
             WAIT(BAR(B_FULL_W + sl), sph);
             tc_fence_after();
-            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * p.chunk_bytes) >> 4) & 0x3FFFu) | b_lbo;
+            const uint32_t b_org = (((sbase + p.off_w + (uint32_t)sl * STEM_CHUNK_BYTES) >> 4) & 0x3FFFu) | b_lbo;
             if (leader) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int tp = c * 4 + j;                 // 0..14: (by, bz pair); 15: zero-weight filler
+              for (int j = 0; j < TPC; ++j) {
+                const int tp = c * TPC + j;               // 0..14: (by, bz pair); 15: zero-weight filler
                 const int by = tp < 15 ? tp / 3 - 2 : 0;
                 const int bz0 = tp < 15 ? (tp % 3) * 2 - 2 : 0;
                 MMA(d_mine, desc_hi | (((a_org + (uint32_t)(by * pitch_y + bz0)) & 0x3FFFu) | a_lbo_scene),
@@ -323,14 +330,14 @@ __global__ void __launch_bounds__(128) stem_s2d_simt_kernel(const __grid_constan
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   const uint4* wq = reinterpret_cast<const uint4*>(p.w);
   const int nh = 128 / p.cg, hf = col0 / nh, colh = col0 - hf * nh;   // CTA-pair blobs are half-major
-  const size_t half_u4 = (size_t)STEM_N_CHUNKS * p.chunk_bytes / 16;
+  const size_t half_u4 = STEM_W_BYTES / p.cg / 16;
   for (int s = 0; s < STEM_FEAT_STAGES; ++s) {
     const int ox = (s >> 2) - 3, py = (s >> 1) & 1, pz = s & 1;
     const int bx = ox >> 1, plane0 = (((ox & 1) << 2) | (s & 3)) * 4;
     for (int tp = 0; tp < 16; ++tp) {
       const int by = (tp >> 2) - 1 - py, bz = (tp & 3) - 1 - pz;
       const int64_t qs = q + (int64_t)bx * p.ls.pitch_x + (int64_t)by * p.ls.pitch_y + bz;
-      const uint4* wt = wq + (size_t)hf * half_u4 + ((size_t)(s * STEM_FEAT_CHUNKS) * p.chunk_bytes + (size_t)tp * (8192 / p.cg)) / 16;   // [kchunk 4][nh][8]
+      const uint4* wt = wq + (size_t)hf * half_u4 + (size_t)(s * 16 + tp) * (STEM_FEAT_TAP_BYTES / p.cg) / 16;   // [kchunk 4][nh][8]
       for (int g = 0; g < 4; ++g) {
         float a[8];
         unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)(plane0 + g) * p.ls.plane_stride + qs) * 8), a);
@@ -348,8 +355,7 @@ __global__ void __launch_bounds__(128) stem_s2d_simt_kernel(const __grid_constan
     const int bx = s - 2;
     for (int tp = 0; tp < 15; ++tp) {
       const int by = tp / 3 - 2, bz0 = (tp % 3) * 2 - 2;
-      const uint4* wt = wq + (size_t)hf * half_u4 + ((size_t)(STEM_FEAT_STAGES * STEM_FEAT_CHUNKS + s * STEM_SCENE_CHUNKS) * p.chunk_bytes +
-                              (size_t)tp * (4096 / p.cg)) / 16;                                              // [kchunk 2][nh][8]
+      const uint4* wt = wq + (size_t)hf * half_u4 + (STEM_SCENE_OFF + (size_t)(s * 16 + tp) * STEM_SCENE_TAP_BYTES) / p.cg / 16;   // [kchunk 2][nh][8]
       for (int c2 = 0; c2 < 2; ++c2) {
         const int64_t qs = q + (int64_t)bx * p.ls.pitch_x + (int64_t)by * p.ls.pitch_y + bz0 + c2;
         float a[8];
@@ -391,7 +397,6 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   p.bias = (const float*)((const char*)d_blob + op.b_offset);
   p.ls = op.lay_src; p.ld = op.lay_dst; p.batch = batch; p.relu = (op.flags & SCENEEGO_F_RELU) ? 1 : 0;
   p.cg = op.cta_pair == 2 ? 2 : 1;
-  p.chunk_bytes = STEM_CHUNK_BYTES / p.cg;
   SE_REQUIRE(p.src && p.dst, "v2v_run: op %d has a null buffer", op_index);
   if (simt) {
     const int V = p.ld.side;
@@ -414,15 +419,15 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   int stages = STEM_MAX_STAGES, slots = 0;
   for (; stages >= 2; --stages) {
     const uint32_t used = 4u * p.win_bytes * stages + fixed;
-    if (used + 3u * p.chunk_bytes > kMaxSmem) continue;
-    slots = (int)((kMaxSmem - used) / p.chunk_bytes);
+    if (used + 3u * STEM_CHUNK_BYTES > kMaxSmem) continue;
+    slots = (int)((kMaxSmem - used) / STEM_CHUNK_BYTES);
     if (slots > STEM_MAX_WSLOTS) slots = STEM_MAX_WSLOTS;
     break;
   }
   SE_REQUIRE(stages >= 2 && slots >= 3, "v2v_run: op %d: stem windows do not fit shared memory (side %d)", op_index, p.ld.side);
   p.win_stages = stages; p.w_slots = slots;
   p.off_w = 4u * p.win_bytes * stages;
-  p.off_bias = p.off_w + (uint32_t)slots * p.chunk_bytes;
+  p.off_bias = p.off_w + (uint32_t)slots * STEM_CHUNK_BYTES;
   p.off_bar = p.off_bias + 128;
   p.n_items = (int)((n_pos + STEM_L - 1) / STEM_L);
   static bool configured = false;
@@ -456,16 +461,16 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
 
 using namespace sceneego;
 
-extern "C" size_t sceneego_v2v_stem_s2d_weight_bytes(void) { return (size_t)STEM_N_CHUNKS * STEM_CHUNK_BYTES; }
+extern "C" size_t sceneego_v2v_stem_s2d_weight_bytes(void) { return STEM_W_BYTES; }
 
 extern "C" int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_bias, const float* h_gamma,
                                           const float* h_beta, const float* h_mean, const float* h_var, double eps,
                                           int n_split, uint16_t* h_w_out, float* h_b_out) {
   SE_REQUIRE(h_weight && h_w_out && h_b_out && (n_split == 1 || n_split == 2), "pack_stem_s2d: bad argument");
   const int NHp = 128 / n_split;                                    // columns per half-blob
-  const size_t half_elems = (size_t)STEM_N_CHUNKS * STEM_CHUNK_BYTES / 2 / n_split;
+  const size_t half_elems = STEM_W_BYTES / 2 / n_split;
   constexpr int CO = 16, CI = 33, K = 7;
-  memset(h_w_out, 0, (size_t)STEM_N_CHUNKS * STEM_CHUNK_BYTES);
+  memset(h_w_out, 0, STEM_W_BYTES);
   double scale[CO];
   for (int co = 0; co < CO; ++co) {
     double sc = 1.0, sh = 0.0;
@@ -486,8 +491,8 @@ extern "C" int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_
     for (int tp = 0; tp < 16; ++tp) {
       const int by = (tp >> 2) - 1 - py, bz = (tp & 3) - 1 - pz;
       const int oy = 2 * by + py, oz = 2 * bz + pz;
-      // within a half-blob: chunk stride 16 KB / n_split, tap stride 8 KB / n_split, [kchunk 4][NHp][8]
-      uint16_t* dst = h_w_out + ((size_t)(s * STEM_FEAT_CHUNKS) * STEM_CHUNK_BYTES + (size_t)tp * 8192) / 2 / n_split;
+      // within a half-blob: tap stride 8 KB / n_split, [kchunk 4][NHp][8]
+      uint16_t* dst = h_w_out + (size_t)(s * 16 + tp) * STEM_FEAT_TAP_BYTES / 2 / n_split;
       for (int n = 0; n < 128; ++n) {
         const int sx = n >> 6, sy = (n >> 5) & 1, sz = (n >> 4) & 1, co = n & 15;
         const int hf = n / NHp, nn = n % NHp;
@@ -501,8 +506,7 @@ extern "C" int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_
     const int bx = s - 2;
     for (int tp = 0; tp < 15; ++tp) {
       const int by = tp / 3 - 2, bz0 = (tp % 3) * 2 - 2;
-      uint16_t* dst = h_w_out + ((size_t)(STEM_FEAT_STAGES * STEM_FEAT_CHUNKS + s * STEM_SCENE_CHUNKS) * STEM_CHUNK_BYTES +
-                                 (size_t)tp * 4096) / 2 / n_split;
+      uint16_t* dst = h_w_out + (STEM_SCENE_OFF + (size_t)(s * 16 + tp) * STEM_SCENE_TAP_BYTES) / 2 / n_split;
       for (int c2 = 0; c2 < 2; ++c2)
         for (int n = 0; n < 128; ++n) {
           const int sx = n >> 6, sy = (n >> 5) & 1, sz = (n >> 4) & 1, co = n & 15;

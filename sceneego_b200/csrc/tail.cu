@@ -50,10 +50,12 @@ __device__ __forceinline__ void load_b(const __nv_bfloat16* w, int cout, int g, 
 
 // One hidden layer on a 16-row tile: a (2 k-tiles) -> relu(a W^T + bias) as the next layer's A fragments.
 __device__ __forceinline__ void hidden_layer(const uint32_t (&a)[2][4], const uint32_t (&b)[4][2][2],
-                                             const float (&bias)[4][2], uint32_t (&out)[2][4]) {
+                                             const float* bias /* shared: this thread's column pair of n-tile 0 */,
+                                             uint32_t (&out)[2][4]) {
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    float c[4] = {bias[nt][0], bias[nt][1], bias[nt][0], bias[nt][1]};
+    const float2 bv = *reinterpret_cast<const float2*>(bias + nt * 8);
+    float c[4] = {bv.x, bv.y, bv.x, bv.y};
     mma_bf16_16816(c, a[0], b[nt][0][0], b[nt][0][1]);
     mma_bf16_16816(c, a[1], b[nt][1][0], b[nt][1][1]);
     // accumulator (rows g / g+8, cols 8nt + 2q, +1) == A fragment slots of k-tile nt/2: even nt -> a0,a1; odd -> a2,a3
@@ -62,35 +64,34 @@ __device__ __forceinline__ void hidden_layer(const uint32_t (&a)[2][4], const ui
   }
 }
 
-__global__ void __launch_bounds__(256) tail_mlp_kernel(const __grid_constant__ TailParams p) {
+__global__ void __launch_bounds__(256, 2) tail_mlp_kernel(const __grid_constant__ TailParams p) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   uint32_t B1[4][2][2], B2[4][2][2], B3[2][2][2];
   load_b<4>(p.w1, 32, g, q, B1);
   load_b<4>(p.w2, 32, g, q, B2);
   load_b<2>(p.w3, 16, g, q, B3);
-  float bias1[4][2], bias2[4][2], bias3[2][2];
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    bias1[nt][0] = p.b1[nt * 8 + 2 * q]; bias1[nt][1] = p.b1[nt * 8 + 2 * q + 1];
-    bias2[nt][0] = p.b2[nt * 8 + 2 * q]; bias2[nt][1] = p.b2[nt * 8 + 2 * q + 1];
-  }
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) { bias3[nt][0] = p.b3[nt * 8 + 2 * q]; bias3[nt][1] = p.b3[nt * 8 + 2 * q + 1]; }
+  __shared__ __align__(8) float s_bias[80];      // b1 | b2 | b3 (registers go to the A tiles in flight instead)
+  if (threadIdx.x < 80) s_bias[threadIdx.x] = threadIdx.x < 32 ? p.b1[threadIdx.x] : threadIdx.x < 64 ? p.b2[threadIdx.x - 32] : p.b3[threadIdx.x - 64];
+  __syncthreads();
+  const float* bias1 = s_bias + 2 * q;
+  const float* bias2 = s_bias + 32 + 2 * q;
+  const float* bias3 = s_bias + 64 + 2 * q;
 
   const int S = p.ls.side;
   const size_t N3 = (size_t)S * S * S;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t n_chunks = (p.n_pos + 31) / 32;
+  constexpr int TPI = 4;                                  // 16-row tiles per warp iteration: 64 positions, 4 KB in flight
+  const int64_t n_chunks = (p.n_pos + 16 * TPI - 1) / (16 * TPI);
   const uint32_t* src32 = reinterpret_cast<const uint32_t*>(p.src);
   const int64_t plane32 = p.ls.plane_stride * 4;          // plane stride in 4-byte words
   for (int64_t ch = warp_global; ch < n_chunks; ch += n_warps) {
-    const int64_t q0 = (int64_t)p.ls.guard + ch * 32;
-    // A fragments of both 16-row tiles: rows (g, g+8) of tile t, 4-byte word q of the row's cell in plane 2kt / 2kt+1
-    uint32_t a[2][2][4];
+    const int64_t q0 = (int64_t)p.ls.guard + ch * (16 * TPI);
+    // A fragments of the 16-row tiles: rows (g, g+8) of tile t, 4-byte word q of the row's cell in plane 2kt / 2kt+1
+    uint32_t a[TPI][2][4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
+    for (int t = 0; t < TPI; ++t)
 #pragma unroll
       for (int kt = 0; kt < 2; ++kt) {
         const int64_t w0 = (q0 + t * 16 + g) * 4 + q + (int64_t)(2 * kt) * plane32;
@@ -100,14 +101,15 @@ __global__ void __launch_bounds__(256) tail_mlp_kernel(const __grid_constant__ T
         a[t][kt][3] = __ldcs(src32 + w0 + plane32 + 8 * 4);
       }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < TPI; ++t) {
       uint32_t h1[2][4], h2[2][4];
       hidden_layer(a[t], B1, bias1, h1);
       hidden_layer(h1, B2, bias2, h2);
       float c[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        c[nt][0] = bias3[nt][0]; c[nt][1] = bias3[nt][1]; c[nt][2] = bias3[nt][0]; c[nt][3] = bias3[nt][1];
+        const float2 bv = *reinterpret_cast<const float2*>(bias3 + nt * 8);
+        c[nt][0] = bv.x; c[nt][1] = bv.y; c[nt][2] = bv.x; c[nt][3] = bv.y;
         mma_bf16_16816(c[nt], h2[0], B3[nt][0][0], B3[nt][0][1]);
         mma_bf16_16816(c[nt], h2[1], B3[nt][1][0], B3[nt][1][1]);
       }
@@ -201,7 +203,7 @@ int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
     SE_CUDA_LAUNCH_CHECK("tail_mlp_simt");
     return SCENEEGO_OK;
   }
-  const int64_t n_chunks = (p.n_pos + 31) / 32;
+  const int64_t n_chunks = (p.n_pos + 63) / 64;
   int64_t blocks = (n_chunks + 7) / 8;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   tail_mlp_kernel<<<(int)blocks, 256, 0, st>>>(p);
