@@ -198,7 +198,9 @@ typedef struct sceneego_v2v_op {
 
 /* Host-side fold + repack (replaces nn.BatchNorm3d eval, v2v.py:13,26,29,37,62, at load time).
  *   h_weight: Conv3d (cout,cin,k,k,k) fp32, or ConvTranspose3d (cin,cout,2,2,2) if transposed
- *   bn_*: NULL for no BatchNorm.  Output: bf16 [tap][cin_pad/8][cout_pad][8] and fp32 bias.
+ *   bn_*: NULL for no BatchNorm.  Output: bf16 [tap][cin_pad/8][cout_pad][8] and fp32 bias
+ *   (transposed: the 8 output parities in groups of npar = min(8, 256/cout_pad) stacked along N,
+ *   [group][cin_pad/8][npar*cout_pad][8], one wide GEMM per group).
  *   xstack > 1: Toeplitz-stacked for x-stacking, [(k+xstack-1)*k*k][cin_pad/8][xstack*cout_pad][8]:
  *   column block s of input-plane offset dxp holds W[dx = dxp - s] (zero where out of range).
  *   n_split = 2 (CTA pairs): the N columns are split in two halves, each a complete blob of its own,

@@ -430,6 +430,7 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   p.off_bias = p.off_w + (uint32_t)slots * STEM_CHUNK_BYTES;
   p.off_bar = p.off_bias + 128;
   p.n_items = (int)((n_pos + STEM_L - 1) / STEM_L);
+  const size_t smem_bytes = (size_t)p.off_bar + 256;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(stem_s2d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
@@ -442,7 +443,7 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * (groups < kNumSMs / 2 ? groups : kNumSMs / 2))); cfg.blockDim = dim3(STEM_THREADS);
-    cfg.dynamicSmemBytes = kMaxSmem; cfg.stream = st;
+    cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
@@ -451,7 +452,7 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
     if (e != cudaSuccess) { set_error("stem_s2d_tc (CTA pair): %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
   } else {
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-    stem_s2d_tc_kernel<1><<<grid, STEM_THREADS, kMaxSmem, st>>>(p);
+    stem_s2d_tc_kernel<1><<<grid, STEM_THREADS, smem_bytes, st>>>(p);
   }
   SE_CUDA_LAUNCH_CHECK("stem_s2d_tc");
   return SCENEEGO_OK;

@@ -649,7 +649,11 @@ __global__ void __launch_bounds__(128) deconv2_kernel(const __grid_constant__ Co
   for (int g = 0; g < p.cin_planes; ++g) {
     float a[8];
     unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8), a);
-    const uint4* wrow = reinterpret_cast<const uint4*>(p.w) + ((size_t)tap * p.cin_planes + g) * p.N + go * 8;
+    // weights: [group of npar parities][cin/8][npar * cout][8]   (p.N = cout here)
+    int npar = 256 / p.N;
+    if (npar > 8) npar = 8;
+    const uint4* wrow = reinterpret_cast<const uint4*>(p.w) +
+                        ((size_t)(tap / npar) * p.cin_planes + g) * ((size_t)npar * p.N) + (size_t)(tap % npar) * p.N + go * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float wv[8];
@@ -793,6 +797,14 @@ extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias
         const uint16_t wv = f2bf((float)((double)h_weight[src] * scale));
         // tap t = (dx, dy, dz); output-plane shift s reads input plane offset dxp = dx + s
         const int dx = t / kk, rest = t % kk;
+        if (transposed) {
+          // output parity t belongs to launch group t / npar; inside a group the parities are stacked along N
+          int npar = 256 / cout_pad;
+          if (npar > 8) npar = 8;
+          const size_t grp = (size_t)t / npar, nrow = (size_t)(t % npar) * cout_pad + co;
+          h_w_out[((grp * (cin_pad / 8) + ci / 8) * ((size_t)npar * cout_pad) + nrow) * 8 + (ci & 7)] = wv;
+          continue;
+        }
         for (int sft = 0; sft < xstack; ++sft) {
           const size_t tp = (size_t)(dx + sft) * kk + rest;
           const size_t col = (size_t)sft * cout_pad + co;
@@ -852,7 +864,7 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)conv_threads(p.tiles));
-    cfg.dynamicSmemBytes = kMaxSmem; cfg.stream = st;
+    cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
@@ -860,7 +872,9 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e != cudaSuccess) { set_error("conv_tc (CTA pair): %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
   } else {
-    fn<<<grid, conv_threads(p.tiles), kMaxSmem, st>>>(p);
+    // only the bytes the plan uses: leaves room for a small concurrent kernel (the output-#2 materialisation on a
+    // side stream) to share the SM
+    fn<<<grid, conv_threads(p.tiles), (size_t)smem, st>>>(p);
   }
   SE_CUDA_LAUNCH_CHECK("conv_tc");
   ++g_launches;
@@ -916,14 +930,15 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
         ++g_launches;
         continue;
       }
-      // tensor path: 8 parities as taps, 256 / cout parities (TMEM columns) per launch
+      // tensor path: the parities do not shift the rows, so `npar` of them (256 / cout columns of TMEM) are
+      // ONE wide GEMM: a single N = npar*cout MMA per K step against weights packed [group][cin/8][npar*cout][8]
       int npar = 256 / op.cout;
       if (npar > 8) npar = 8;
       const __nv_bfloat16* w_all = p.w;
       for (int par0 = 0; par0 < 8; par0 += npar) {
         ConvParams q = p;
-        q.k = 1; q.r = 0; q.xs = 1; q.n0 = op.cout; q.mma_n = op.cout; q.N = npar * op.cout; q.n_dx = 1;
-        q.deconv = 1; q.par0 = par0; q.taps_dx = npar;
+        q.k = 1; q.r = 0; q.xs = 1; q.n0 = op.cout; q.mma_n = npar * op.cout; q.N = npar * op.cout; q.n_dx = 1;
+        q.deconv = 1; q.par0 = par0; q.taps_dx = 1;
         q.w = w_all + (size_t)par0 * q.cin_planes * op.cout * 8;
         const int rc = launch_conv_tc(q, batch, i, st);
         if (rc != SCENEEGO_OK) return rc;

@@ -321,9 +321,11 @@ class V2VModel(nn.Module):
     def _res(self, pg: _Program, blk: Res3DBlock, x: int, level: int) -> int:
         xs = self.c32_xstack if blk.res_branch[0].out_channels == 32 else 1
         # CTA pairs (tcgen05 cta_group::2) where the B operand's shared-memory read bounds the MMA: N = 64
-        cg = self.cta_pair if (xs * blk.res_branch[0].out_channels == 64 and level <= 1 and blk.res_branch[0].in_channels >= 32) else 1
+        wide = xs * blk.res_branch[0].out_channels == 64 and level <= 1
+        cg = self.cta_pair if wide else 1
+        cg0 = cg if blk.res_branch[0].in_channels >= 32 else 1
         t = pg.acquire(level)
-        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs, cta_pair=cg)
+        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs, cta_pair=cg0)
         if len(blk.skip_con) > 0:
             s = pg.acquire(level)
             pg.conv(blk.skip_con[0], blk.skip_con[1], x, s, relu=False)

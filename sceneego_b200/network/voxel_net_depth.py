@@ -117,6 +117,7 @@ class VoxelNetwork_depth(nn.Module):
         cv = self.coord_volume
         self._axis = torch.stack([cv[:, 0, 0, 0], cv[0, :, 0, 1], cv[0, 0, :, 2]]).contiguous()
         self.last_launches = 0
+        self._side_stream = None
 
     def build_coord_volume(self):
         """network/voxel_net_depth.py:110-134, on the device (fp32, mul then add)."""
@@ -140,12 +141,27 @@ class VoxelNetwork_depth(nn.Module):
         feat32 = _lib.feature_conv1x1(feat, conv.weight, conv.bias)           # (B,64,64,32) channel-last
         launches = 1
         features = None
+        feat_done = None
         if self.materialize_features:
-            features = _lib.features_upsample_pad(feat32, self.image_height,
-                                                  (self.image_width - self.image_height) // 2)
+            # output #2 of the reference is a pure HBM write (168 MB/frame) nothing downstream reads: it runs on a
+            # side stream and shares the SMs (and the idle HBM bandwidth) with the tensor-bound V2V kernels
+            main = torch.cuda.current_stream(feat.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=feat.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                features = _lib.features_upsample_pad(feat32, self.image_height,
+                                                      (self.image_width - self.image_height) // 2)
+                feat_done = torch.cuda.Event()
+                feat_done.record(side)
+            feat32.record_stream(side)
+            features.record_stream(main)
             launches += 1
         if self.with_scene is True and scene_volumes is None and depth_map_batch is None:
             print("no scene volume or depth input!")
+            if feat_done is not None:
+                torch.cuda.current_stream(feat.device).wait_event(feat_done)
             return None
         grid = None
         if not self.fused_projection:
@@ -178,6 +194,8 @@ class VoxelNetwork_depth(nn.Module):
         kp, volumes = _lib.softargmax3d(logits, float(self.volume_multiplier), bool(self.volume_softmax),
                                         self._axis, None, self.materialize_volumes)
         launches += 3 if self.materialize_volumes else 2
+        if feat_done is not None:
+            torch.cuda.current_stream(feat.device).wait_event(feat_done)
         self.last_launches = launches
         return kp, features, volumes, self.coord_volumes
 

@@ -76,7 +76,13 @@ def test_pack_conv_folds_batchnorm():
                                           k, tr, cout_p, cin_p, 1, 1, p(wp), p(bp)) == 0
         scale = gamma.astype(np.float64) / np.sqrt(var.astype(np.float64) + 1e-5)
         wf = (w.transpose(1, 0, 2, 3, 4) if tr else w).reshape(cout, cin, taps) * scale[:, None, None]
-        got = _unpack(wp, taps, cin_p, cout_p)
+        if tr:   # transposed: parities stacked along N in groups of npar = min(8, 256 / cout_pad)
+            npar = min(8, 256 // cout_p)
+            a = wp.reshape(taps // npar, cin_p // 8, npar, cout_p, 8)
+            f = (a.astype(np.uint32) << 16).view(np.float32)
+            got = f.transpose(3, 1, 4, 0, 2).reshape(cout_p, cin_p, taps)
+        else:
+            got = _unpack(wp, taps, cin_p, cout_p)
         ref = torch.from_numpy(wf.astype(np.float32)).to(torch.bfloat16).float().numpy()
         assert np.array_equal(got[:cout, :cin], ref)                 # bf16 round-to-nearest-even, bit-exact
         assert np.all(got[cout:] == 0) and np.all(got[:, cin:] == 0)  # channel padding is zero
