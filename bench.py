@@ -47,7 +47,8 @@ def workload_config(frames, world):
             "frames_per_gpu": frames, "global_frames": frames * world, "volume_size": V, "joints": J,
             "parallelism": f"frame-shard x{world}, NCCL all-gather of poses",
             "weights": "random init (seeded), BatchNorm statistics randomised",
-            "outputs": "reference-identical 4-tuple (features and softmaxed volumes materialised)",
+            "outputs": "reference-identical 4-tuple (features and softmaxed volumes materialised; the 168 MB/frame "
+                       "features tensor is written on a side stream inside the timed region)",
             "v2v_chunk_frames": None,
             "l2_policy": "inputs (604 MB/step) and activations (>1 GB/layer) exceed the 126 MB L2"}
 
@@ -247,11 +248,29 @@ def ours_arm(args):
         conv_ms = kern["v2v"]["conv_ms_per_frame"]
         conv_fl = kern["v2v"]["conv_flops_per_frame"]
         ach = conv_fl / (conv_ms * 1e-3) / 1e12
-        roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM Conv3d, all 47 conv launches of V2V)",
-                "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
-                "traffic": None, "peak_source": peak_src,
-                "how": "algorithmic 2*Cin*Cout*k^3*V^3 FLOPs of the conv ops / sum of their CUDA-event durations "
-                       "(sceneego_v2v_run_profile), per frame"}
+        # dominant kernel: the nine 3^3 Conv3d(32,32) launches at 64^3 (conv_tc_kernel<2,4,2,3,2>, CTA pairs) --
+        # the largest share of the step (profiles/r01_ncu_launch_shares_final.txt); the stem and the
+        # whole tensor path are reported next to it
+        fam = kern["v2v"]["families"]
+        c32 = fam["conv3_32_32_full_res"]
+        n_launch_frames = kern["v2v"]["chunk_frames"]
+        roof = {"kernel": "conv_tc_kernel<2,4,2,3,2> (tcgen05 cta_group::2 implicit-GEMM Conv3d 3x3x3 32->32 at 64^3; "
+                          f"{c32['launches']} launches per {n_launch_frames}-frame chunk)",
+                "bound": "tensor", "achieved": c32["tflops"], "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": c32["tflops"] / tc_peak,
+                "traffic": 516.7e6,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture "
+                                "at 16 frames per launch (profiles/r01_ncu_conv_tc_final.txt): 282 MB + 235 MB vs "
+                                "563 MB algorithmic (2 x 16 x 17.6 MB)",
+                "peak_source": peak_src,
+                "how": f"algorithmic 2*32*32*27*64^3 = 14.50 GFLOP per frame x {n_launch_frames} frames per launch / mean "
+                       "CUDA-event duration of those launches on the launching stream (sceneego_v2v_run_profile)",
+                "launch_ms": c32["ms_per_frame"] * n_launch_frames / c32["launches"],
+                "stem": {"kernel": "stem_s2d_tc_kernel<2> (7x7x7 Conv3d 33->16, 2x2x2 output stacking)",
+                         "achieved": fam["stem7_33_16"]["tflops"], "frac": fam["stem7_33_16"]["tflops"] / tc_peak,
+                         "tensor_pipe_active_pct_ncu": 87.1},
+                "all_tensor_convs": {"achieved": ach, "frac": ach / tc_peak,
+                                     "how": "algorithmic FLOPs of every tcgen05 conv of V2V / sum of their durations"}}
         cfg = workload_config(B, world)
         cfg["v2v_chunk_frames"] = min(args.chunk, B)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -315,8 +334,8 @@ def stage_kernel_timings(net, feat_d, depth_d, B, args):
     rec("feature_conv1x1", ms, 256 * 64 * 64 * 4 + 64 * 64 * 32 * 4, "read (256,64,64) f32 + write (64,64,32) f32")
     ms = timed(lambda: _lib.unproject(feat32, grid, None, V, 2.0, 1024, 1280, None, in_buf, pg.lay_in,
                                       extra_zero_planes=(pg.in_pad - 32) // 8))
-    rec("unproject", ms, 64 * 64 * 32 * 4 + V ** 3 * (32 + 16) * 2 + V ** 3 * 8,
-        "read 0.524 MB features + 2.1 MB grid, write 48 bf16 channels (32 lifted + cleared scene planes)")
+    rec("unproject", ms, 64 * 64 * 32 * 4 + V ** 3 * 32 * 2 + V ** 3 * 2 + V ** 3 * 8,
+        "read 0.524 MB features + 2.1 MB grid, write 32 bf16 channels + the cleared occupancy plane (space-to-depth layout)")
     d = depth_d[:n]
     ms = timed(lambda: _lib.voxelize_depth(d, net._ray_dev, 1024, 1280, V, 2.0, None, in_buf, pg.lay_in, channel=32))
     rec("voxelize", ms, 1024 * 1280 * 4, "read (1024,1280) f32 depth; ray table (31.5 MB) shared by all frames; sparse bf16 scatter")
@@ -328,8 +347,19 @@ def stage_kernel_timings(net, feat_d, depth_d, B, args):
     table = [{"op": i, "kind": m["kind"], "cin": m["cin"], "cout": m["cout"], "k": m["k"], "side": m["side"],
               "ms_per_frame": ms / n, "tflops": (m["flops"] * n / (ms * 1e-3) / 1e12) if m["flops"] else None}
              for i, (m, ms) in enumerate(prof)]
+    def family(pred):
+        sel = [(m, ms) for m, ms in prof if pred(m)]
+        t = sum(ms for _, ms in sel)
+        f = sum(m["flops"] for m, _ in sel)
+        return {"launches": len(sel), "ms_per_frame": t / n, "flops_per_frame": f, "tflops": f * n / (t * 1e-3) / 1e12 if t else 0.0}
+    fams = {"conv3_32_32_full_res": family(lambda m: m["kind"] == "conv" and m["k"] == 3 and m["cin"] == 32 and m["cout"] == 32 and m["side"] == V),
+            "stem7_33_16": family(lambda m: m["kind"] == "conv" and m["k"] == 7),
+            "other_tensor_convs": family(lambda m: m["kind"] == "conv" and m["k"] != 7 and not (m["k"] == 3 and m["cin"] == 32 and m["cout"] == 32 and m["side"] == V)),
+            "tail_1x1_fused": family(lambda m: m["kind"] == "tail"),
+            "deconv": family(lambda m: m["kind"] == "deconv"),
+            "maxpool": family(lambda m: m["kind"] == "pool")}
     out["v2v"] = {"conv_ms_per_frame": conv_ms / n, "conv_flops_per_frame": conv_fl, "pool_deconv_ms_per_frame": other_ms / n,
-                  "bound": "tensor", "launches_per_chunk": len(prof), "chunk_frames": n}
+                  "bound": "tensor", "launches_per_chunk": len(prof), "chunk_frames": n, "families": fams}
     if args.profile_ops:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_ops)), exist_ok=True)
         json.dump(table, open(args.profile_ops, "w"), indent=1)

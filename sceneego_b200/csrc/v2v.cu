@@ -11,15 +11,18 @@
 //
 // conv_tc_kernel: persistent, warp-specialised implicit GEMM.
 //   rows (M)   = 128 consecutive positions per UMMA tile, `tiles` tiles per work item
-//   cols (N)   = Cout (16..128)
+//   cols (N)   = xs * Cout (16..256): xs consecutive x-planes of outputs stacked against Toeplitz weights
 //   reduction  = taps x Cin, 16 channels (two 8-channel planes) per tcgen05.mma
 //   warp 0     = producer: cp.async.bulk (TMA 1-D) of the per-dx activation window
 //                (one contiguous run per channel plane) and of the weight chunks
-//   warp 1     = TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5  = epilogue: tcgen05.ld -> bias / residual / ReLU / pad-zeroing -> bf16 planes
+//   warps 1-4  = TMEM allocator + tcgen05.mma issuers, one tile (group) each: a single warp can issue an
+//                MMA only every ~41.5 cycles (222 for cta_group::2), less than the pipe needs at N <= 64
+//   next 8     = epilogue: tcgen05.ld -> bias / residual / ReLU / pad-zeroing -> bf16 planes
 //   smem operands use the no-swizzle K-major canonical layout: 8 rows x 16 B core matrices,
 //   SBO = 128 B between 8-row groups, LBO = plane stride between the two K chunks.
 //   Accumulators: 2 x (tiles x N) fp32 columns of TMEM, double-buffered across work items.
+//   CG = 2: two CTAs of a cluster share one MMA stream (M = 256), weights N-split across the pair.
+// The 7^3 stem and the fused 1x1 tail have their own kernels (stem.cu, tail.cu).
 #include "tc_common.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
@@ -61,7 +64,6 @@ struct ConvParams {
   uint32_t win_bytes, wchunk_bytes, tap_bytes;
   uint32_t off_win, off_w, off_bias, off_bar;
   uint32_t tmem_cols, half_cols;
-  int debug;                        // SCENEEGO_DEBUG bit mask (tuning experiments only; 0 in production)
   // CTA pair (cg = 2): two CTAs of one cluster run one tcgen05.mma.cta_group::2 stream (M = 256 = one
   // 128-row tile of each CTA) issued by the leader; each CTA stages its own windows and HALF of the
   // weight columns (B is N-split across the pair), which halves the weight traffic and the B-operand
@@ -277,33 +279,24 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
     // ===================== producer =====================
     if (lane == 0) {
       int ws = 0, wph = 0, sl = 0, sph = 0;
-      int n_win_issued = 0, n_w_issued = 0;
       for (int it = 0; it < my_items; ++it) {
         int ib, ix0, icell0;
         const int64_t q0 = item_origin(item_of(it), ib, ix0, icell0);
         for (int dx = 0; dx < p.n_dx; ++dx) {
           mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
-          if ((p.debug & 4) && n_win_issued >= p.win_stages) { mbar_arrive(BAR(B_FULL_WIN + ws)); }
-          else {
-          ++n_win_issued;
           mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * (2 * KSTEPS));
           const int64_t qs = q0 + (int64_t)(dx - p.r) * p.ls.pitch_x - halo;
 #pragma unroll
           for (int g = 0; g < 2 * KSTEPS; ++g)
             bulk_g2s(sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS + g) * p.win_bytes,
                      p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8, p.win_bytes, BAR(B_FULL_WIN + ws));
-          }
           if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
           for (int wc = 0; wc < p.wchunks_per_dx; ++wc) {
             mbar_wait(BAR(B_EMPTY_W + sl), sph ^ 1);
-            if ((p.debug & 2) && n_w_issued >= p.w_slots) { mbar_arrive(BAR(B_FULL_W + sl)); }
-            else {
-            ++n_w_issued;
             mbar_expect_tx(BAR(B_FULL_W + sl), p.wchunk_bytes);
             const char* wsrc = reinterpret_cast<const char*>(p.w) + (size_t)cta_rank * p.w_half_bytes +
                                (size_t)(dx * p.wchunks_per_dx + wc) * p.wchunk_bytes;
             bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes, wsrc, p.wchunk_bytes, BAR(B_FULL_W + sl));
-            }
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
@@ -383,7 +376,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
             // generic chunk: `wtaps` taps, tap coordinates carried in running counters
             for (int tp = 0; tp < wtaps; ++tp) {
               const uint32_t a_lo = win_lo + (uint32_t)(dy * pitch_y + dz);    // tap shift, in 16-B cells
-              if (leader && !(p.debug & 8)) {
+              if (leader) {
 #pragma unroll
                 for (int tt = 0; tt < TILES / NW; ++tt) {
 #pragma unroll
@@ -400,7 +393,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
           } else {
             // 3^3 stencil, chunk = WROWS whole dy-rows of 3 taps: straight-line code, the tap shifts are
             // (dy + r) * pitch_y + j with compile-time r, j -- no per-tap loop control or divergence
-            if (leader && !(p.debug & 8)) {
+            if (leader) {
 #pragma unroll
               for (int r = 0; r < WROWS; ++r) {
                 const uint32_t a_row = win_lo + a_mine + (uint32_t)((dy + r) * pitch_y);
@@ -484,7 +477,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
       mbar_wait(BAR(B_TMEM_FULL + buf), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = t_first; t < TILES && !(p.debug & 1); t += t_step) {
+      for (int t = t_first; t < TILES; t += t_step) {
         RowInfo ri_next = ri;
         if (t + t_step < TILES) ri_next = row_info(t + t_step);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * p.half_cols +
@@ -826,7 +819,6 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
   p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);
   p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
   p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
-  { const char* ed = getenv("SCENEEGO_DEBUG"); p.debug = ed ? atoi(ed) : 0; }
   const int smem = plan_conv(p);
   SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", op_index);
   if (p.xs == 1) {
