@@ -233,6 +233,15 @@ def ours_arm(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = total * args.steps / (float(ms2.item()) / 1000.0)
     assert torch.isfinite(outs[-1]).all()
+    # the host->device copy of one step alone (explains the gap between `value` and `e2e`: PCIe, not kernels)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(3):
+        feat_d.copy_(feat_h, non_blocking=True)
+        depth_d.copy_(depth_h, non_blocking=True)
+    g1.record()
+    barrier()
+    h2d_ms = g0.elapsed_time(g1) / 3
 
     line = None
     if rank == 0:
@@ -279,7 +288,9 @@ def ours_arm(args):
                 "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes // args.steps,
                         "d2h_bytes_per_step": pipe.d2h_bytes // args.steps,
-                        "api": "sceneego_b200.pipeline.HostStagePipeline.run (pinned host -> poses on host)"},
+                        "api": "sceneego_b200.pipeline.HostStagePipeline.run (pinned host -> poses on host)",
+                        "h2d_alone_ms_per_step": h2d_ms,
+                        "h2d_alone_GB_per_s": (feat_h.numel() + depth_h.numel()) * 4 / (h2d_ms * 1e-3) / 1e9},
                 "gpu_launches": launches, "roofline": roof, "kernels": kern,
                 "frames_per_s_per_gpu": value / world}
         if world == 1 and not args.no_cpu_baseline:

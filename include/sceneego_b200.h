@@ -193,6 +193,11 @@ typedef struct sceneego_v2v_op {
                           with n_split = 2; 0/1 = one CTA per tile                          */
   int64_t w_offset;    /* byte offset of the packed bf16 weights in the blob               */
   int64_t b_offset;    /* byte offset of the fp32 bias (cout entries) in the blob          */
+  int32_t src2;        /* conv: second source buffer of a fused 1x1 projection shortcut
+                          (Res3DBlock.skip_con, network/v2v.py:32-43), -1 = none; its packed weights
+                          (pack_conv with ksize 1, the same xstack / n_split) follow the stencil's
+                          inside each (half-)blob, and `bias` is the sum of both folded biases      */
+  int32_t cin2;        /* channels of src2, padded: must be cin / 2                        */
   sceneego_vol_layout_t lay_src, lay_dst;
 } sceneego_v2v_op_t;
 

@@ -41,7 +41,7 @@ class V2VOp(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_int32), ("ksize", C.c_int32), ("cin", C.c_int32),
                 ("cout", C.c_int32), ("cout_real", C.c_int32), ("src", C.c_int32), ("dst", C.c_int32),
                 ("res", C.c_int32), ("impl", C.c_int32), ("xstack", C.c_int32), ("cta_pair", C.c_int32), ("w_offset", C.c_int64),
-                ("b_offset", C.c_int64),
+                ("b_offset", C.c_int64), ("src2", C.c_int32), ("cin2", C.c_int32),
                 ("lay_src", VolLayout), ("lay_dst", VolLayout)]
 
 

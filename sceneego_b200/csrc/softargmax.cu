@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(256) softmax_write_kernel(const float* __restr
 }
 
 static int sa_splits(int BJ, int N, int* chunk_out) {
-  int splits = (4 * kNumSMs + BJ - 1) / BJ;
+  // ~6 CTAs of 256 threads are resident per SM: aim for >= 8 full waves so the last partial wave costs little
+  // (one CTA per joint volume left 960 CTAs = 1.08 waves at B = 64: the tail doubled the time)
+  int splits = (48 * kNumSMs + BJ - 1) / BJ;
   if (splits < 1) splits = 1;
   if (splits > SA_MAX_SPLITS) splits = SA_MAX_SPLITS;
   const int unit = SA_THREADS * 16;  // elements one CTA iteration covers

@@ -70,6 +70,13 @@ struct ConvParams {
   // shared-memory reads that bound N <= 128 MMAs.  Weights are packed half-major: [half][tap][cin/8][N/2][8].
   int cg;
   uint32_t w_half_bytes;            // bytes of one half-blob (cg = 2)
+  // Fused projection shortcut (Res3DBlock.skip_con, network/v2v.py:32-38): a 1x1 conv of a SECOND source with
+  // half the channels, accumulated into the same tile after the stencil taps -- n_dx2 = xs extra stages of one
+  // tap each (input plane x0 + e feeds output plane block e).  Weights follow the stencil's inside (each half
+  // of) the blob; the two folded biases are summed on the host.
+  const __nv_bfloat16* src2;
+  int n_dx2;
+  uint32_t w_main_bytes;            // bytes of the stencil weights per (half-)blob = offset of the shortcut taps
 };
 
 constexpr int CONV_EPI_WARPS = 8;
@@ -300,6 +307,25 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
+        if constexpr (KSTEPS % 2 == 0) {
+          for (int e = 0; e < p.n_dx2; ++e) {          // fused 1x1 shortcut: KSTEPS planes of src2, one tap
+            mbar_wait(BAR(B_EMPTY_WIN + ws), wph ^ 1);
+            mbar_expect_tx(BAR(B_FULL_WIN + ws), p.win_bytes * KSTEPS);
+            const int64_t qs = q0 + (int64_t)e * p.ls.pitch_x - halo;
+#pragma unroll
+            for (int g = 0; g < KSTEPS; ++g)
+              bulk_g2s(sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS + g) * p.win_bytes,
+                       p.src2 + ((int64_t)g * p.ls.plane_stride + qs) * 8, p.win_bytes, BAR(B_FULL_WIN + ws));
+            if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+            mbar_wait(BAR(B_EMPTY_W + sl), sph ^ 1);
+            mbar_expect_tx(BAR(B_FULL_W + sl), p.tap_bytes / 2);
+            bulk_g2s(sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes,
+                     reinterpret_cast<const char*>(p.w) + (size_t)cta_rank * p.w_half_bytes + p.w_main_bytes +
+                         (size_t)e * (p.tap_bytes / 2),
+                     p.tap_bytes / 2, BAR(B_FULL_W + sl));
+            if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+          }
+        }
       }
     }
   } else if (warp <= NW) {
@@ -314,7 +340,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
       // leader's full barriers, in consumption order; warps 2..NW have nothing to do.
       if (warp == 1 && lane == 0) {
         int ws = 0, wph = 0, sl = 0, sph = 0;
-        for (int it = 0; it < my_items; ++it)
+        for (int it = 0; it < my_items; ++it) {
           for (int dx = 0; dx < p.n_dx; ++dx) {
             mbar_wait(BAR(B_FULL_WIN + ws), wph);
             mbar_arrive_remote(mapa_shared(BAR(B_FULL_WIN + ws), 0));
@@ -325,6 +351,15 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
               if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
             }
           }
+          for (int e = 0; e < p.n_dx2; ++e) {          // shortcut stages
+            mbar_wait(BAR(B_FULL_WIN + ws), wph);
+            mbar_arrive_remote(mapa_shared(BAR(B_FULL_WIN + ws), 0));
+            if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+            mbar_wait(BAR(B_FULL_W + sl), sph);
+            mbar_arrive_remote(mapa_shared(BAR(B_FULL_W + sl), 0));
+            if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+          }
+        }
       }
     } else {
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -420,6 +455,29 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
         if (leader) COMMIT(BAR(B_EMPTY_WIN + ws));
         if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
       }
+      if constexpr (KSTEPS % 2 == 0) {
+        for (int e = 0; e < p.n_dx2; ++e) {            // fused 1x1 shortcut: centre tap of the second source
+          WAIT(BAR(B_FULL_WIN + ws), wph);
+          WAIT(BAR(B_FULL_W + sl), sph);
+          tc_fence_after();
+          const uint32_t a_c = ((((sbase + p.off_win + (uint32_t)(ws * 2 * KSTEPS) * p.win_bytes) >> 4) & 0x3FFFu) | a_lo_flags) +
+                               a_mine + (uint32_t)(p.r * (pitch_y + 1));
+          const uint32_t b_c = (((sbase + p.off_w + (uint32_t)sl * p.wchunk_bytes) >> 4) & 0x3FFFu) | b_lo_flags;
+          if (leader) {
+#pragma unroll
+            for (int tt = 0; tt < TILES / NW; ++tt) {
+#pragma unroll
+              for (int ks = 0; ks < KSTEPS / 2; ++ks)
+                MMA(d_mine + (uint32_t)(tt * NW) * n_cols, desc_hi | (a_c + (uint32_t)(tt * NW) * 128u + (uint32_t)ks * a_ks_step),
+                    desc_hi | (b_c + (uint32_t)ks * b_ks_step), idesc, 1u);
+            }
+          }
+          if (leader) COMMIT(BAR(B_EMPTY_W + sl));
+          if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
+          if (leader) COMMIT(BAR(B_EMPTY_WIN + ws));
+          if (++ws == p.win_stages) { ws = 0; wph ^= 1; }
+        }
+      }
       if (leader) COMMIT(BAR(B_TMEM_FULL + buf));
     }
     __syncwarp();
@@ -468,6 +526,40 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
         return XS == 1 ? decode_row(p, q0 + r) : decode_row_plane(p, ib, ix0, icell0 + r);
       };
       RowInfo ri = row_info(t_first);
+      if constexpr (TILES == 1) {
+        // single-tile items (transposed convs: N = 256 against 128 rows; the deep, small levels) are short, so the
+        // residual / skip cells of FOUR column chunks are kept in flight -- one chunk ahead left the 64->32
+        // transposed conv latency-bound at ~1 TB/s on its skip tensor
+        constexpr int D = 4;
+        uint4 q0r[D], q1r[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          q0r[d] = make_uint4(0, 0, 0, 0); q1r[d] = q0r[d];
+          const int c = c_first + d * c_step;
+          if (c < nch) { int chn; const RowInfo rp = shifted(ri, ix0, c, chn); load_res16(p, rp, chn, q0r[d], q1r[d]); }
+        }
+        mbar_wait(BAR(B_TMEM_FULL + buf), (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * p.half_cols;
+        int cpf = c_first + D * c_step;
+#pragma unroll 1
+        for (int c = c_first; c < nch; c += c_step) {
+          const uint4 r0 = q0r[0], r1 = q1r[0];
+#pragma unroll
+          for (int d = 0; d + 1 < D; ++d) { q0r[d] = q0r[d + 1]; q1r[d] = q1r[d + 1]; }
+          if (cpf < nch) { int chn; const RowInfo rp = shifted(ri, ix0, cpf, chn); load_res16(p, rp, chn, q0r[D - 1], q1r[D - 1]); }
+          cpf += c_step;
+          int ch0;
+          const RowInfo rs = shifted(ri, ix0, c, ch0);
+          uint32_t raw[16];
+          tc_ld16(taddr + (uint32_t)(c << 4), raw);
+          tc_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          store_row16_pre(p, rs, ch0, v, s_bias, r0, r1);
+        }
+      } else {
       uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
       if (c_first < nch) {
         int ch0;
@@ -497,6 +589,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
           store_row16_pre(p, rs, ch0, v, s_bias, r0, r1);
         }
         ri = ri_next;
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -594,6 +687,23 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
             }
           }
         }
+  }
+  if (ri.valid && p.n_dx2 > 0) {   // fused 1x1 shortcut of the second source (column block 0 of its first tap)
+    const int nh = p.cg == 2 ? p.N / 2 : p.N, hf = c0 / nh;
+    const int planes2 = p.cin_planes / 2;
+    for (int g = 0; g < planes2; ++g) {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.src2 + ((int64_t)g * p.ls.plane_stride + q) * 8), a);
+      const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.w) + (size_t)hf * p.w_half_bytes + p.w_main_bytes) +
+                          (size_t)g * nh + (c0 - hf * nh);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float wv[8];
+        unpack8(__ldg(wrow + j), wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], wv[i], acc[j]);
+      }
+    }
   }
   store_row16(p, ri, c0, acc, s_bias);
 }
@@ -830,8 +940,9 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
   }
   int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
   conv_tc_fn fn = nullptr;
+  p.w_main_bytes = (uint32_t)(p.n_dx * p.taps_dx) * p.tap_bytes;
+  p.w_half_bytes = p.w_main_bytes + (uint32_t)p.n_dx2 * (p.tap_bytes / 2);
   if (p.cg == 2) {
-    p.w_half_bytes = (uint32_t)(p.n_dx * p.taps_dx) * p.tap_bytes;
     const int groups = (p.n_items + 1) / 2;
     grid = 2 * (groups < kNumSMs / 2 ? groups : kNumSMs / 2);
     fn = pick_conv_tc_pair(p.ksteps, p.tiles, p.xs, p.wrows);
@@ -948,9 +1059,19 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
     p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
     p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
     p.cg = op.cta_pair == 2 ? 2 : 1;
+    p.src2 = nullptr; p.n_dx2 = 0;
+    if (op.src2 >= 0 && op.cin2 > 0) {
+      SE_REQUIRE(op.cin2 * 2 == op.cin && (op.cin / 16) % 2 == 0 && op.ksize == 3 && d_buffers[op.src2],
+                 "v2v_run: op %d: a fused shortcut needs a 3^3 conv and a second source with half its channels", i);
+      p.src2 = (const __nv_bfloat16*)d_buffers[op.src2];
+      p.n_dx2 = op.xstack > 1 ? op.xstack : 1;
+    }
     if (op.impl == 1 || force_simt) {
-      p.n0 = op.cout; p.N = (op.xstack > 1 ? op.xstack : 1) * op.cout;   // weight row stride of the stacked blob
-      p.w_half_bytes = (uint32_t)((op.ksize + (op.xstack > 1 ? op.xstack : 1) - 1) * op.ksize * op.ksize) * p.cin_planes * (p.N / 2) * 16u;
+      const int xs_ = op.xstack > 1 ? op.xstack : 1;
+      p.n0 = op.cout; p.N = xs_ * op.cout;   // weight row stride of the stacked blob
+      const uint32_t tapb = (uint32_t)p.cin_planes * (p.N / p.cg) * 16u;
+      p.w_main_bytes = (uint32_t)((op.ksize + xs_ - 1) * op.ksize * op.ksize) * tapb;
+      p.w_half_bytes = p.w_main_bytes + (uint32_t)p.n_dx2 * (tapb / 2);
       dim3 grid((unsigned)((n_pos + 127) / 128), op.cout / 16);
       conv_simt_kernel<<<grid, 128, 0, st>>>(p, n_pos);
       SE_CUDA_LAUNCH_CHECK("conv_simt");

@@ -179,20 +179,34 @@ class _Program:
 
     # -- ops -----------------------------------------------------------------
     def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False,
-             xstack: int = 1, cta_pair: int = 1):
+             xstack: int = 1, cta_pair: int = 1, shortcut=None):
+        """shortcut = (conv1x1, bn, src2): the projection shortcut of a Res3DBlock (v2v.py:32-43) accumulated into
+        the same GEMM tile instead of being written out and re-read as a residual."""
         k = conv.kernel_size[0]
         cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
-        w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad, xstack, cta_pair)
+        if shortcut is None:
+            w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad, xstack, cta_pair)
+        else:
+            sc_conv, sc_bn, _ = shortcut
+            assert k == 3 and res < 0 and sc_conv.kernel_size[0] == 1 and _pad16(sc_conv.in_channels) * 2 == cin_pad
+            w_main, b_main = self.pack_arrays(conv, bn, cin_pad, cout_pad, xstack, cta_pair)
+            w_sc, b_sc = self.pack_arrays(sc_conv, sc_bn, cin_pad // 2, cout_pad, xstack, cta_pair)
+            wm, ws = w_main.reshape(cta_pair, -1), w_sc.reshape(cta_pair, -1)     # half-major blobs
+            w_off = self._append_blob(np.concatenate([np.concatenate([wm[h], ws[h]]) for h in range(cta_pair)]))
+            b_off = self._append_blob((b_main.astype(np.float64) + b_sc.astype(np.float64)).astype(np.float32))
         op = _lib.V2VOp()
         op.type = _lib.OP_CONV
         op.flags = (_lib.F_RELU if relu else 0) | (_lib.F_RESIDUAL if res >= 0 else 0) | (_lib.F_OUT_F32 if out_f32 else 0)
         op.ksize, op.cin, op.cout, op.cout_real = k, cin_pad, cout_pad, conv.out_channels
         op.src, op.dst, op.res, op.impl, op.xstack, op.cta_pair = src, dst, res, 0, xstack, cta_pair
         op.w_offset, op.b_offset = w_off, b_off
+        op.src2, op.cin2 = (shortcut[2], cin_pad // 2) if shortcut is not None else (-1, 0)
         op.lay_src = self.lay_of(src)
         op.lay_dst = self.lay_of(dst) if not out_f32 else self.lay_of(src)
         self.ops.append(op)
         fl = 2 * conv.in_channels * conv.out_channels * k ** 3 * op.lay_src.side ** 3
+        if shortcut is not None:
+            fl += 2 * shortcut[0].in_channels * shortcut[0].out_channels * op.lay_src.side ** 3
         self.flops += fl
         self.meta.append(dict(kind="conv", cin=conv.in_channels, cout=conv.out_channels, k=k,
                               side=op.lay_src.side, flops=fl))
@@ -216,6 +230,7 @@ class _Program:
                                                    int(cta_pair), fp(w_out), fp(b_out)), "v2v_pack_stem_s2d")
         op = _lib.V2VOp()
         op.type, op.flags = _lib.OP_STEM7_S2D, _lib.F_RELU
+        op.src2, op.cin2 = -1, 0
         op.ksize, op.cin, op.cout, op.cout_real = 7, 33, 16, 16
         op.src, op.dst, op.res, op.impl, op.xstack, op.cta_pair = src, dst, -1, 0, 1, cta_pair
         op.w_offset, op.b_offset = self._append_blob(w_out), self._append_blob(b_out)
@@ -237,6 +252,7 @@ class _Program:
         assert seg.size == 2048 + 2048 + 1024 + 4 * (32 + 32 + 16)
         op = _lib.V2VOp()
         op.type, op.flags = _lib.OP_TAIL_MLP, _lib.F_OUT_F32
+        op.src2, op.cin2 = -1, 0
         op.ksize, op.cin, op.cout, op.cout_real = 1, 32, 16, out_conv.out_channels
         op.src, op.dst, op.res, op.impl, op.xstack = src, dst, -1, 0, 1
         op.w_offset = self._append_blob(seg)
@@ -252,6 +268,7 @@ class _Program:
     def pool(self, src: int, dst: int, channels: int):
         op = _lib.V2VOp()
         op.type, op.cin, op.cout, op.cout_real = _lib.OP_MAXPOOL2, channels, channels, channels
+        op.src2, op.cin2 = -1, 0
         op.src, op.dst, op.res = src, dst, -1
         op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
         self.ops.append(op)
@@ -262,6 +279,7 @@ class _Program:
         w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad)
         op = _lib.V2VOp()
         op.type = _lib.OP_DECONV2
+        op.src2, op.cin2 = -1, 0
         op.flags = _lib.F_RELU | (_lib.F_ADD_AFTER if add >= 0 else 0)
         op.ksize, op.cin, op.cout, op.cout_real = 2, cin_pad, cout_pad, conv.out_channels
         op.src, op.dst, op.res = src, dst, add
@@ -292,6 +310,7 @@ class V2VModel(nn.Module):
         self.stem_xstack = 4
         self.c32_xstack = 2      # 3^3 convs with Cout = 32: stack two x-planes (N = 64)
         self.fuse_tail = True
+        self.fuse_shortcut = True  # 1x1 projection shortcuts accumulate into the second conv of their Res3DBlock
         self.cta_pair = 2        # 1 = every conv on single CTAs
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
                                           Res3DBlock(32, 32), Res3DBlock(32, 32))
@@ -326,12 +345,18 @@ class V2VModel(nn.Module):
         cg0 = cg if blk.res_branch[0].in_channels >= 32 else 1
         t = pg.acquire(level)
         pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs, cta_pair=cg0)
+        y = pg.acquire(level)
+        if len(blk.skip_con) > 0 and self.fuse_shortcut and blk.skip_con[0].in_channels * 2 == blk.skip_con[0].out_channels:
+            # relu(conv3(t) + bn(conv1(x))): the 1x1 projection of x joins the second conv's accumulation
+            pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, xstack=xs, cta_pair=cg,
+                    shortcut=(blk.skip_con[0], blk.skip_con[1], x))
+            pg.release(t)
+            return y
         if len(blk.skip_con) > 0:
             s = pg.acquire(level)
             pg.conv(blk.skip_con[0], blk.skip_con[1], x, s, relu=False)
         else:
             s = x
-        y = pg.acquire(level)
         pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s, xstack=xs, cta_pair=cg)
         pg.release(t)
         if s != x:

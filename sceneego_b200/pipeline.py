@@ -4,7 +4,8 @@
 loop makes once the backbone features and depth maps live in host memory: every
 batch is copied host->device on a side stream (double-buffered, so the copy of
 batch i+1 overlaps the kernels of batch i), lifted with
-`VoxelNetwork_depth.lift`, and its (B,15,3) poses are copied back.
+`VoxelNetwork_depth.lift`, and its (B,15,3) poses are copied back into pinned buffers that are
+reused by later `run` calls (copy the result out if it must outlive the next call).
 """
 from typing import Iterable, List, Tuple
 
@@ -22,6 +23,7 @@ class HostStagePipeline:
         self.gather_fn = gather_fn
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._host_out = []          # pinned result buffers, reused across run() calls (cudaHostAlloc is slow)
 
     def _stage(self, slot: int, feat: torch.Tensor, depth: torch.Tensor) -> None:
         if not (feat.is_pinned() and depth.is_pinned()):
@@ -54,7 +56,13 @@ class HostStagePipeline:
             if self.gather_fn is not None:
                 kp = self.gather_fn(kp)
             self.done[slot].record(main)
-            host = torch.empty(kp.shape, dtype=kp.dtype, pin_memory=True)
+            if i >= len(self._host_out) or self._host_out[i].shape != kp.shape:
+                buf = torch.empty(kp.shape, dtype=kp.dtype, pin_memory=True)
+                if i < len(self._host_out):
+                    self._host_out[i] = buf
+                else:
+                    self._host_out.append(buf)
+            host = self._host_out[i]
             host.copy_(kp, non_blocking=True)
             self.d2h_bytes += kp.numel() * 4
             out.append(host)

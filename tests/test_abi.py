@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Calib) == 8 * 20 + 8          # 20 doubles + 2 int32
     assert ctypes.sizeof(_lib.VolLayout) == 40               # 6 int32, int64, s2d + reserved
-    assert ctypes.sizeof(_lib.V2VOp) == 12 * 4 + 16 + 2 * 40      # 11 int32 + pad, 2 int64, 2 layouts
+    assert ctypes.sizeof(_lib.V2VOp) == 12 * 4 + 16 + 8 + 2 * 40  # 12 int32, 2 int64, src2 + cin2, 2 layouts
 
 
 def test_host_only_entry_points():

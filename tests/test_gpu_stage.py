@@ -100,3 +100,38 @@ def test_cpu_device_is_rejected():
         VoxelNetwork_depth(util.load_config(), device="cpu")
     with pytest.raises(_lib.SceneEgoError):
         _lib.softargmax3d(torch.zeros(1, 1, 4, 4, 4), 1.0, True, torch.zeros(3, 4), None, False)
+
+
+def test_ragged_chunks_and_v128_configuration(tables64):
+    """Batches that do not divide the V2V chunk (5 frames in chunks of 2, 2, 1) give the poses of the same frames
+    run one chunk at a time; and BASELINE.json configs[3] (128^3 cube) runs through the tensor path and agrees with
+    the CUDA-core checker kernels (the oracle needs minutes per frame at that size)."""
+    from sceneego_b200.network.voxel_net_depth import VoxelNetwork_depth
+    from sceneego_b200.network.v2v import V2VModel
+    torch.manual_seed(0)
+    small = VoxelNetwork_depth(util.load_config(batch_size=2), device="cuda", v2v_chunk=2).eval()
+    _load(small, "random_bn", 1.0)
+    feat = synth.synthetic_features(5, seed=9).cuda()
+    depth = synth.synthetic_depth_room(5, tables64.ray, seed=2).cuda()
+    with torch.no_grad():
+        all5 = small.lift(feat, small.grid_coord_proj_batch, small.coord_volumes, depth_map_batch=depth)[0]
+        last = small.lift(feat[4:5], small.grid_coord_proj_batch, small.coord_volumes, depth_map_batch=depth[4:5])[0]
+    assert all5.shape == (5, 15, 3) and torch.allclose(all5[4], last[0], atol=1e-6)
+    del small
+    m = V2VModel(33, 15).eval()
+    sd = synth.synthetic_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=2, mode="random_bn")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x = torch.randn(1, 33, 128, 128, 128, generator=torch.Generator().manual_seed(1)).abs()
+    x[:, 32] = (x[:, 32] > 1.2).float()
+    x = x.cuda()
+    pg = m.program(128, 1, x.device)
+    from sceneego_b200 import _lib
+    _lib.pack_volume(x, pg.buffers[pg.in_buf], pg.lay_in)
+    a = torch.empty(1, 15, 128, 128, 128, device="cuda")
+    b = torch.empty_like(a)
+    m.run_chunk(pg, 1, a, impl=0)
+    m.run_chunk(pg, 1, b, impl=1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all()
+    assert ((a - b).norm() / b.norm()).item() <= 2e-2

@@ -136,6 +136,33 @@ def test_cta_pair_conv(cin, cout, k, S, B, xs):
     assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
 
 
+@pytest.mark.parametrize("c,S,B,xs,pair", [(32, 16, 3, 2, 2), (32, 16, 2, 2, 1), (64, 16, 2, 1, 2), (128, 8, 2, 1, 1), (32, 64, 1, 2, 2)])
+def test_fused_projection_shortcut(c, S, B, xs, pair):
+    """Res3DBlock with a 1x1 projection shortcut (network/v2v.py:32-43): relu(bn(conv3(t)) + bn(conv1(x))) as ONE op --
+    the shortcut's taps join the stencil's accumulation (second source with half the channels)."""
+    conv, bn = _mk_conv(c, c, 3, seed=3 * c)
+    sc_conv, sc_bn = _mk_conv(c // 2, c, 1, seed=5 * c)
+    g = torch.Generator().manual_seed(S + B + c)
+    t_in = util.bf16_round(torch.randn(B, c, S, S, S, generator=g)).cuda()
+    x_in = util.bf16_round(torch.randn(B, c // 2, S, S, S, generator=g)).cuda()
+    got, dst, lay = util.run_single_op(t_in, conv, bn, relu=True, impl=0, xstack=xs, cta_pair=pair,
+                                       shortcut=(sc_conv, sc_bn, x_in))
+    with torch.no_grad():
+        ref = F.relu(bn(conv(t_in)) + sc_bn(sc_conv(x_in)))
+    _close(got, ref, f"fused shortcut c{c} S{S} xs{xs} pair{pair}")
+    simt, _, _ = util.run_single_op(t_in, conv, bn, relu=True, impl=1, xstack=xs, cta_pair=pair,
+                                    shortcut=(sc_conv, sc_bn, x_in))
+    assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()
+    plane = dst[0].float()
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(S, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
+
+
 @pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("V,B", [(16, 2), (32, 3), (64, 1)])
 def test_stem_s2d(V, B, pair):

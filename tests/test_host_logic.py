@@ -31,7 +31,7 @@ def test_program_structure_and_flops():
     assert abs(V2VModel(32, 15).flops_per_frame(64) / 1e9 - 296.2) < 0.1
     pg = m.program(32, 2, torch.device("cpu"))
     kinds = [op.type for op in pg.ops]
-    assert kinds.count(_lib.OP_CONV) == 43 and kinds.count(_lib.OP_TAIL_MLP) == 1 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
+    assert kinds.count(_lib.OP_CONV) == 40 and kinds.count(_lib.OP_TAIL_MLP) == 1 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
     assert kinds[0] == _lib.OP_STEM7_S2D
     assert pg.flops * 8 == m.flops_per_frame(64)
     assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 33 and pg.ops[0].cout == 16
@@ -42,8 +42,11 @@ def test_program_structure_and_flops():
     assert last.type == _lib.OP_TAIL_MLP and last.flags & _lib.F_OUT_F32 and last.cout_real == 15 and last.cout == 16
     # every op reads a buffer some earlier op (or the input staging) wrote, and never its own output
     written = {pg.in_buf}
+    assert sum(1 for op in pg.ops if op.src2 >= 0) == 3           # 16->32, 32->64, 64->128 projection shortcuts fused
     for op in pg.ops:
         assert op.src in written and op.src != op.dst
+        if op.src2 >= 0:
+            assert op.src2 in written and op.src2 != op.dst and op.cin2 * 2 == op.cin
         if op.res >= 0:
             assert op.res in written and op.res != op.dst
         written.add(op.dst)

@@ -39,7 +39,8 @@ def unpack_bits(packed, V):
     return np.unpackbits(packed)[: V ** 3].reshape(V, V, V).astype(np.float32)
 
 
-def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None, xstack=1, cta_pair=1):
+def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None, xstack=1, cta_pair=1,
+                  shortcut=None):
     """Run one V2V op (conv or deconv) through sceneego_v2v_run; x (B,Cin,S,S,S) f32 cuda."""
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program, _pad16
@@ -66,13 +67,21 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
         bufs.append(rb)
         lays.append(lay_d)
         r_idx = 2
+    sc = None
+    if shortcut is not None:      # (conv1x1, bn, x2): second source with half the channels, same layout as src
+        sc_conv, sc_bn, x2 = shortcut
+        sb = _lib.alloc_volume(lay_s, _pad16(x2.shape[1]), x.device)
+        _lib.pack_volume(x2.contiguous(), sb, lay_s)
+        bufs.append(sb)
+        lays.append(lay_s)
+        sc = (sc_conv, sc_bn, len(bufs) - 1)
     pg.buffers = bufs
     pg.buf_level = [0] * len(bufs)
     pg.lay_of = lambda i: lays[i]
     if deconv:
         pg.deconv(conv, bn, 0, 1, add=r_idx)
     else:
-        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack, cta_pair=cta_pair)
+        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack, cta_pair=cta_pair, shortcut=sc)
     pg.ops[0].impl = impl
     pg.finalize()
     global LAST_PROGRAM
