@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCENEEGO_ABI_VERSION 2
+#define SCENEEGO_ABI_VERSION 3
 
 enum {
   SCENEEGO_OK = 0,
@@ -168,7 +168,13 @@ enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2,
        SCENEEGO_OP_TAIL_MLP = 4    /* back_layers[1], back_layers[2] and output_layer (three 1x1 convs,
                                       network/v2v.py:150-161,168-169) in one pass; blob segment at w_offset:
                                       [w1 32x32][w2 32x32][w3 32x16] bf16 (pack_conv layout), then
-                                      [b1 32][b2 32][b3 16] f32; dst = (B,cout_real,S,S,S) f32 */ };
+                                      [b1 32][b2 32][b3 16] f32; dst = (B,cout_real,S,S,S) f32 */,
+       SCENEEGO_OP_CONV3_MARCH = 5 /* Conv3d k3 + folded BN (+ residual / ReLU / fused projection shortcut) with
+                                      3*cout <= 256 as an x-marching banded GEMM (csrc/march.cu): the three dx taps of
+                                      an input plane are one N = 3*cout MMA into a ring of tensor-memory slots, the
+                                      weights stay resident in shared memory.  Weights from
+                                      sceneego_v2v_pack_conv_march; a fused shortcut's follow in the plain ksize-1
+                                      sceneego_v2v_pack_conv layout.  xstack / cta_pair are ignored */ };
 enum {
   SCENEEGO_F_RELU = 1,         /* ReLU after bias (+ residual)                              */
   SCENEEGO_F_RESIDUAL = 2,     /* add buffer `res` before the ReLU (Res3DBlock, v2v.py:40-43) */
@@ -214,6 +220,15 @@ int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias, const flo
                            const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
                            double eps, int cout, int cin, int ksize, int transposed, int cout_pad,
                            int cin_pad, int xstack, int n_split, uint16_t* h_w_out, float* h_b_out);
+
+/* Fold + repack for SCENEEGO_OP_CONV3_MARCH: h_weight (cout,cin,3,3,3) fp32 -> bf16
+ *   [tap (dy,dz)][cin_pad/8][3*cout_pad][8], row block j holding W[dx = 2 - j] (the block that feeds output
+ *   plane x - 1 + j from input plane x), 27*cin_pad*cout_pad elements, and cout_pad fp32 biases.  The fold is
+ *   the one of sceneego_v2v_pack_conv. */
+int sceneego_v2v_pack_conv_march(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
+                                 const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
+                                 double eps, int cout, int cin, int cout_pad, int cin_pad, uint16_t* h_w_out,
+                                 float* h_b_out);
 
 /* Same for the 7^3 stem read from a space-to-depth source (SCENEEGO_OP_STEM7_S2D):
  *   h_weight (16,33,7,7,7) fp32.  Output: sceneego_v2v_stem_s2d_weight_bytes() bytes of bf16 in the

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
-    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d",
+    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march",
 ]
 
 
@@ -45,7 +45,7 @@ class V2VOp(C.Structure):
                 ("lay_src", VolLayout), ("lay_dst", VolLayout)]
 
 
-OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D, OP_TAIL_MLP = 0, 1, 2, 3, 4
+OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D, OP_TAIL_MLP, OP_CONV3_MARCH = 0, 1, 2, 3, 4, 5
 F_RELU, F_RESIDUAL, F_ADD_AFTER, F_OUT_F32 = 1, 2, 4, 8
 
 _lib = None
@@ -71,7 +71,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sceneego_vol_layout_make_s2d.restype = C.c_int64
     lib.sceneego_v2v_stem_s2d_weight_bytes.restype = C.c_size_t
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
-    if lib.sceneego_abi_version() != 2:
+    if lib.sceneego_abi_version() != 3:
         raise SceneEgoError("libsceneego_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

@@ -79,5 +79,7 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
                     bool simt, cudaStream_t st);
 int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
                     bool simt, cudaStream_t st);
+int launch_conv_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
+                      cudaStream_t st);
 
 }  // namespace sceneego

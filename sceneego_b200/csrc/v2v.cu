@@ -77,6 +77,7 @@ struct ConvParams {
   const __nv_bfloat16* src2;
   int n_dx2;
   uint32_t w_main_bytes;            // bytes of the stencil weights per (half-)blob = offset of the shortcut taps
+  int march;                        // checker only: weights in the marching layout [tap(dy,dz)][cin/8][3*n0][8] (march.cu)
 };
 
 constexpr int CONV_EPI_WARPS = 8;
@@ -676,8 +677,10 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
             unpack8(*reinterpret_cast<const uint4*>(p.src + ((int64_t)g * p.ls.plane_stride + qs) * 8), a);
             // p.N = xs*n0 columns; CTA-pair blobs are packed half-major ([half][tap][cin/8][N/2][8])
             const int nh = p.cg == 2 ? p.N / 2 : p.N, hf = c0 / nh;
-            const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.w) + (size_t)hf * p.w_half_bytes) +
-                                ((size_t)tap * p.cin_planes + g) * nh + (c0 - hf * nh);
+            const uint4* wrow = p.march
+                ? reinterpret_cast<const uint4*>(p.w) + ((size_t)(dy * 3 + dz) * p.cin_planes + g) * (3 * p.n0) + (2 - dx) * p.n0 + c0
+                : reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.w) + (size_t)hf * p.w_half_bytes) +
+                      ((size_t)tap * p.cin_planes + g) * nh + (c0 - hf * nh);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float wv[8];
@@ -1046,6 +1049,29 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
         const int rc = launch_conv_tc(q, batch, i, st);
         if (rc != SCENEEGO_OK) return rc;
       }
+      continue;
+    }
+    if (op.type == SCENEEGO_OP_CONV3_MARCH) {
+      if (op.impl == 1 || force_simt) {
+        // checker: the generic CUDA-core conv reading the marching weight layout
+        SE_REQUIRE(op.ksize == 3 && op.cin % 16 == 0 && op.cout % 16 == 0, "v2v_run: op %d bad marching conv", i);
+        p.k = 3; p.r = 1; p.xs = 1; p.n0 = op.cout; p.N = op.cout; p.cg = 1; p.march = 1;
+        p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);
+        p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
+        p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
+        p.src2 = nullptr; p.n_dx2 = 0;
+        if (op.src2 >= 0 && op.cin2 > 0) { p.src2 = (const __nv_bfloat16*)d_buffers[op.src2]; p.n_dx2 = 1; }
+        p.w_main_bytes = 27u * (uint32_t)p.cin_planes * (uint32_t)op.cout * 16u;
+        p.w_half_bytes = 0;
+        const int64_t n_pos = (int64_t)batch * p.ls.frame_pitch;
+        dim3 grid((unsigned)((n_pos + 127) / 128), op.cout / 16);
+        conv_simt_kernel<<<grid, 128, 0, st>>>(p, n_pos);
+        SE_CUDA_LAUNCH_CHECK("conv_simt (march layout)");
+      } else {
+        const int rc = launch_conv_march(op, d_buffers, d_blob, batch, i, st);
+        if (rc != SCENEEGO_OK) return rc;
+      }
+      ++g_launches;
       continue;
     }
     SE_REQUIRE(op.type == SCENEEGO_OP_CONV, "v2v_run: op %d unknown type", i);

@@ -150,7 +150,7 @@ class _Program:
         return self._append_blob(w_out), self._append_blob(b_out)
 
     def pack_arrays(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
-                    xstack: int = 1, n_split: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+                    xstack: int = 1, n_split: int = 1, march: bool = False) -> Tuple[np.ndarray, np.ndarray]:
         transposed = isinstance(conv, nn.ConvTranspose3d)
         w = conv.weight.detach().float().cpu().contiguous().numpy()
         k = w.shape[-1]
@@ -171,6 +171,14 @@ class _Program:
         else:
             g = bt = mu = var = None
             eps = 0.0
+        if march:
+            # marching layout (csrc/march.cu): [tap(dy,dz)][cin/8][3*cout][8], no Toeplitz zeros
+            assert k == 3 and not transposed and xstack == 1 and n_split == 1
+            rc = _lib.load_library().sceneego_v2v_pack_conv_march(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var),
+                                                                  C.c_double(eps), cout, cin, cout_pad, cin_pad,
+                                                                  fp(w_out), fp(b_out))
+            _lib._check(rc, "v2v_pack_conv_march")
+            return w_out, b_out
         rc = _lib.load_library().sceneego_v2v_pack_conv(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var),
                                                         C.c_double(eps), cout, cin, k, int(transposed), cout_pad,
                                                         cin_pad, int(xstack), int(n_split), fp(w_out), fp(b_out))
@@ -179,12 +187,25 @@ class _Program:
 
     # -- ops -----------------------------------------------------------------
     def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False,
-             xstack: int = 1, cta_pair: int = 1, shortcut=None):
+             xstack: int = 1, cta_pair: int = 1, shortcut=None, march: bool = False):
         """shortcut = (conv1x1, bn, src2): the projection shortcut of a Res3DBlock (v2v.py:32-43) accumulated into
-        the same GEMM tile instead of being written out and re-read as a residual."""
+        the same GEMM tile instead of being written out and re-read as a residual.
+        march: run as SCENEEGO_OP_CONV3_MARCH (x-marching banded GEMM, csrc/march.cu); xstack / cta_pair unused."""
         k = conv.kernel_size[0]
         cin_pad, cout_pad = _pad16(conv.in_channels), _pad16(conv.out_channels)
-        if shortcut is None:
+        if march:
+            assert k == 3 and not out_f32 and cout_pad == conv.out_channels
+            xstack = cta_pair = 1
+            w_main, b_main = self.pack_arrays(conv, bn, cin_pad, cout_pad, march=True)
+            if shortcut is None:
+                w_off, b_off = self._append_blob(w_main), self._append_blob(b_main)
+            else:
+                sc_conv, sc_bn, _ = shortcut
+                assert res < 0 and sc_conv.kernel_size[0] == 1 and _pad16(sc_conv.in_channels) * 2 == cin_pad
+                w_sc, b_sc = self.pack_arrays(sc_conv, sc_bn, cin_pad // 2, cout_pad)
+                w_off = self._append_blob(np.concatenate([w_main, w_sc]))
+                b_off = self._append_blob((b_main.astype(np.float64) + b_sc.astype(np.float64)).astype(np.float32))
+        elif shortcut is None:
             w_off, b_off = self.pack(conv, bn, cin_pad, cout_pad, xstack, cta_pair)
         else:
             sc_conv, sc_bn, _ = shortcut
@@ -195,7 +216,7 @@ class _Program:
             w_off = self._append_blob(np.concatenate([np.concatenate([wm[h], ws[h]]) for h in range(cta_pair)]))
             b_off = self._append_blob((b_main.astype(np.float64) + b_sc.astype(np.float64)).astype(np.float32))
         op = _lib.V2VOp()
-        op.type = _lib.OP_CONV
+        op.type = _lib.OP_CONV3_MARCH if march else _lib.OP_CONV
         op.flags = (_lib.F_RELU if relu else 0) | (_lib.F_RESIDUAL if res >= 0 else 0) | (_lib.F_OUT_F32 if out_f32 else 0)
         op.ksize, op.cin, op.cout, op.cout_real = k, cin_pad, cout_pad, conv.out_channels
         op.src, op.dst, op.res, op.impl, op.xstack, op.cta_pair = src, dst, res, 0, xstack, cta_pair
@@ -312,6 +333,7 @@ class V2VModel(nn.Module):
         self.fuse_tail = True
         self.fuse_shortcut = True  # 1x1 projection shortcuts accumulate into the second conv of their Res3DBlock
         self.cta_pair = 2        # 1 = every conv on single CTAs
+        self.march = True        # 3^3 convs with Cout = 32: x-marching banded GEMM (csrc/march.cu) instead of x-stacking
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
                                           Res3DBlock(32, 32), Res3DBlock(32, 32))
         self.encoder_decoder = EncoderDecorder()
@@ -343,13 +365,14 @@ class V2VModel(nn.Module):
         wide = xs * blk.res_branch[0].out_channels == 64 and level <= 1
         cg = self.cta_pair if wide else 1
         cg0 = cg if blk.res_branch[0].in_channels >= 32 else 1
+        mr = self.march and blk.res_branch[0].out_channels == 32
         t = pg.acquire(level)
-        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs, cta_pair=cg0)
+        pg.conv(blk.res_branch[0], blk.res_branch[1], x, t, relu=True, xstack=xs, cta_pair=cg0, march=mr)
         y = pg.acquire(level)
         if len(blk.skip_con) > 0 and self.fuse_shortcut and blk.skip_con[0].in_channels * 2 == blk.skip_con[0].out_channels:
             # relu(conv3(t) + bn(conv1(x))): the 1x1 projection of x joins the second conv's accumulation
             pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, xstack=xs, cta_pair=cg,
-                    shortcut=(blk.skip_con[0], blk.skip_con[1], x))
+                    shortcut=(blk.skip_con[0], blk.skip_con[1], x), march=mr)
             pg.release(t)
             return y
         if len(blk.skip_con) > 0:
@@ -357,7 +380,7 @@ class V2VModel(nn.Module):
             pg.conv(blk.skip_con[0], blk.skip_con[1], x, s, relu=False)
         else:
             s = x
-        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s, xstack=xs, cta_pair=cg)
+        pg.conv(blk.res_branch[3], blk.res_branch[4], t, y, relu=True, res=s, xstack=xs, cta_pair=cg, march=mr)
         pg.release(t)
         if s != x:
             pg.release(s)

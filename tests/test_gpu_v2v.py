@@ -163,6 +163,62 @@ def test_fused_projection_shortcut(c, S, B, xs, pair):
     assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
 
 
+def _pads_clean(dst, lay, S, B):
+    plane = dst[0].float()
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(S, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    return plane[mask].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,S,B,res", [(32, 32, 16, 3, True), (32, 32, 16, 2, False), (16, 32, 16, 2, False),
+                                              (32, 32, 32, 5, True), (32, 32, 64, 1, True), (16, 32, 64, 1, False),
+                                              (32, 16, 8, 2, True), (32, 32, 2, 3, True), (32, 32, 40, 2, True)])
+def test_marching_conv(cin, cout, S, B, res):
+    """SCENEEGO_OP_CONV3_MARCH (csrc/march.cu): x-marching banded GEMM, resident weights, ring of accumulator
+    slots (B > 1 and S = 40 make the ring wrap at every phase; S = 2 has only face planes)."""
+    conv, bn = _mk_conv(cin, cout, 3, seed=31 + cin + S)
+    g = torch.Generator().manual_seed(S * 5 + B)
+    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    r = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda() if res else None
+    got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=r, impl=0, march=True)
+    _close(got, _ref(x, conv, bn, True, res=r), f"marching conv {cin}->{cout} S{S}")
+    simt, _, _ = util.run_single_op(x, conv, bn, relu=True, res=r, impl=1, march=True)
+    assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()      # checker reads the marching blob
+    plain, _, _ = util.run_single_op(x, conv, bn, relu=True, res=r, impl=0)
+    assert ((got - plain).abs() <= 0.0079 * plain.abs() + 1e-4).all()    # conv_tc: same math, other summation order
+    assert _pads_clean(dst, lay, S, B), "pad / guard cells were written"
+
+
+@pytest.mark.parametrize("S,B", [(16, 3), (64, 1)])
+def test_marching_conv_fused_shortcut(S, B):
+    """relu(bn(conv3(t)) + bn(conv1(x))) on the marching kernel: the shortcut is one N = Cout MMA per plane."""
+    conv, bn = _mk_conv(32, 32, 3, seed=77)
+    sc_conv, sc_bn = _mk_conv(16, 32, 1, seed=78)
+    g = torch.Generator().manual_seed(S + B)
+    t_in = util.bf16_round(torch.randn(B, 32, S, S, S, generator=g)).cuda()
+    x_in = util.bf16_round(torch.randn(B, 16, S, S, S, generator=g)).cuda()
+    got, dst, lay = util.run_single_op(t_in, conv, bn, relu=True, impl=0, march=True, shortcut=(sc_conv, sc_bn, x_in))
+    with torch.no_grad():
+        ref = F.relu(bn(conv(t_in)) + sc_bn(sc_conv(x_in)))
+    _close(got, ref, f"marching fused shortcut S{S}")
+    simt, _, _ = util.run_single_op(t_in, conv, bn, relu=True, impl=1, march=True, shortcut=(sc_conv, sc_bn, x_in))
+    assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()
+    assert _pads_clean(dst, lay, S, B), "pad / guard cells were written"
+
+
+def test_marching_conv_is_deterministic_and_reuses_buffers():
+    """Two runs over the same buffers give bit-identical results (one issuer, fixed accumulation order)."""
+    conv, bn = _mk_conv(32, 32, 3, seed=5)
+    x = util.bf16_round(torch.randn(4, 32, 32, 32, 32, generator=torch.Generator().manual_seed(2))).cuda()
+    a, _, _ = util.run_single_op(x, conv, bn, relu=True, impl=0, march=True)
+    b, _, _ = util.run_single_op(x, conv, bn, relu=True, impl=0, march=True)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("V,B", [(16, 2), (32, 3), (64, 1)])
 def test_stem_s2d(V, B, pair):

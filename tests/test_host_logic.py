@@ -5,6 +5,7 @@ import ctypes as C
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from sceneego_b200 import _lib
 from sceneego_b200.network import pose_resnet
@@ -31,7 +32,9 @@ def test_program_structure_and_flops():
     assert abs(V2VModel(32, 15).flops_per_frame(64) / 1e9 - 296.2) < 0.1
     pg = m.program(32, 2, torch.device("cpu"))
     kinds = [op.type for op in pg.ops]
-    assert kinds.count(_lib.OP_CONV) == 40 and kinds.count(_lib.OP_TAIL_MLP) == 1 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
+    # ten 3^3 convs with 32 output channels march along x (csrc/march.cu), the other 30 stay on conv_tc
+    assert kinds.count(_lib.OP_CONV3_MARCH) == 10 and all(op.cout == 32 and op.ksize == 3 for op in pg.ops if op.type == _lib.OP_CONV3_MARCH)
+    assert kinds.count(_lib.OP_CONV) == 30 and kinds.count(_lib.OP_TAIL_MLP) == 1 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
     assert kinds[0] == _lib.OP_STEM7_S2D
     assert pg.flops * 8 == m.flops_per_frame(64)
     assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 33 and pg.ops[0].cout == 16
@@ -186,3 +189,53 @@ def test_stem_s2d_packing_reproduces_conv3d():
     assert (out - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()      # bf16 weights (2^-9 relative each)
     # and the blob's non-zero count is exactly the 343 x 33 x 16 taps, each stored once per stacked voxel it serves
     assert int((w_out != 0).sum()) <= 343 * 33 * 16 * 8
+
+
+def test_march_packing_walked_like_the_kernel_reproduces_conv3d():
+    """sceneego_v2v_pack_conv_march: [tap(dy,dz)][cin/8][3*cout][8] with row block j = W[dx = 2 - j].  Walking it the
+    way conv_march_kernel does (input plane x feeds outputs x-1, x, x+1 through row blocks 0, 1, 2; a ring of
+    accumulator slots; N = 2*cout sub-bands at the faces) over bf16 inputs equals Conv3d(k3, pad 1) + BN."""
+    lib = _lib.load_library()
+    torch.manual_seed(5)
+    cin, cout, S = 16, 32, 5
+    conv = nn.Conv3d(cin, cout, 3, padding=1)
+    bn = nn.BatchNorm3d(cout).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1); bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 2)
+    keep = [a.detach().float().contiguous().numpy() for a in
+            (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+    w_out = np.zeros(27 * cin * cout, dtype=np.uint16)
+    b_out = np.zeros(cout, dtype=np.float32)
+    args = [a.ctypes.data_as(C.c_void_p) for a in keep]
+    assert lib.sceneego_v2v_pack_conv_march(*args, C.c_double(bn.eps), cout, cin, cout, cin,
+                                            w_out.ctypes.data_as(C.c_void_p), b_out.ctypes.data_as(C.c_void_p)) == 0
+    wf = (w_out.astype(np.uint32) << 16).view(np.float32).reshape(9, cin // 8, 3 * cout, 8)     # [t][g][row][c8]
+    wm = wf.transpose(0, 2, 1, 3).reshape(9, 3 * cout, cin).astype(np.float64)                  # [t][row][ci]
+    x = torch.randn(1, cin, S, S, S).to(torch.bfloat16).float()
+    xp = np.zeros((cin, S, S + 2, S + 2))
+    xp[:, :, 1:-1, 1:-1] = x[0].numpy()
+    NS = 4                                                   # a short ring so that it wraps inside the march
+    ring = np.zeros((NS, cout, S, S))
+    out = np.zeros((cout, S, S, S))
+    for xin in range(S):
+        j_lo, j_hi = (0 if xin > 0 else 1), (2 if xin + 1 < S else 1)
+        if xin == 0:
+            ring[0] = 0
+        if xin + 1 < S:
+            ring[(xin + 1) % NS] = 0                         # the slot this plane opens
+        for t in range(9):
+            dy, dz = t // 3, t % 3
+            win = xp[:, xin, dy:dy + S, dz:dz + S]           # (ci, y, z)
+            band = np.einsum("rc,cyz->ryz", wm[t, j_lo * cout:(j_hi + 1) * cout], win)
+            for j in range(j_lo, j_hi + 1):
+                ring[(xin - 1 + j) % NS] += band[(j - j_lo) * cout:(j - j_lo + 1) * cout]
+        if xin > 0:
+            out[:, xin - 1] = ring[(xin - 1) % NS]           # complete: committed to the epilogue
+        if xin + 1 == S:
+            out[:, xin] = ring[xin % NS]
+    out += b_out.astype(np.float64)[:, None, None, None]
+    with torch.no_grad():
+        wq = conv.weight * (bn.weight / torch.sqrt(bn.running_var + bn.eps))[:, None, None, None, None]
+        ref = F.conv3d(x.double(), wq.to(torch.bfloat16).double(), padding=1)[0].numpy()
+        ref += ((conv.bias - bn.running_mean) * bn.weight / torch.sqrt(bn.running_var + bn.eps) + bn.bias).double().numpy()[:, None, None, None]
+    assert np.abs(out - ref).max() <= 1e-5

@@ -40,7 +40,7 @@ def unpack_bits(packed, V):
 
 
 def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, add_after=None, xstack=1, cta_pair=1,
-                  shortcut=None):
+                  shortcut=None, march=False):
     """Run one V2V op (conv or deconv) through sceneego_v2v_run; x (B,Cin,S,S,S) f32 cuda."""
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program, _pad16
@@ -81,7 +81,7 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     if deconv:
         pg.deconv(conv, bn, 0, 1, add=r_idx)
     else:
-        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack, cta_pair=cta_pair, shortcut=sc)
+        pg.conv(conv, bn, 0, 1, relu=relu, res=r_idx, xstack=xstack, cta_pair=cta_pair, shortcut=sc, march=march)
     pg.ops[0].impl = impl
     pg.finalize()
     global LAST_PROGRAM
