@@ -92,12 +92,24 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
 
-  const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto item_of = [&](int it, int& b, int& cell0) {
-    const uint32_t item = blockIdx.x + (uint32_t)it * gridDim.x;
+  // Work split: the (item, plane) pairs, item-major, are cut into gridDim.x equal contiguous ranges, so a CTA
+  // marches over [x0, x1) of its first and last item and over all of the others: the load is balanced to one
+  // plane whatever the item count (2112 items on 296 CTAs would otherwise leave 12 % of the machine idle).
+  // A march over [x0, x1) reads input planes max(x0-1, 0) .. min(x1, S-1).
+  const uint32_t total = (uint32_t)p.n_items * (uint32_t)S;
+  const uint32_t base = total / gridDim.x, rem = total % gridDim.x;
+  const uint32_t P0 = blockIdx.x * base + (blockIdx.x < rem ? blockIdx.x : rem);
+  const uint32_t P1 = P0 + base + (blockIdx.x < rem ? 1u : 0u);
+  const uint32_t first_item = P1 > P0 ? P0 / (uint32_t)S : 0u, last_item = P1 > P0 ? (P1 - 1) / (uint32_t)S : 0u;
+  const int my_items = P1 > P0 ? (int)(last_item - first_item + 1) : 0;
+  auto item_of = [&](int it, int& b, int& cell0, int& x0, int& x1) {
+    const uint32_t item = first_item + (uint32_t)it;
     b = (int)fdiv(item, p.fd_tpp);
     cell0 = (int)(item - (uint32_t)b * (uint32_t)p.tiles_per_plane) * MARCH_L;
+    x0 = it == 0 ? (int)(P0 - first_item * (uint32_t)S) : 0;
+    x1 = item == last_item ? (int)(P1 - last_item * (uint32_t)S) : S;
   };
+  constexpr uint32_t G_START = 4u * NS;   // running output counter; the offset keeps (G - 2) non-negative, slot 0 / parity 0
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -110,10 +122,11 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
       }
       int ws = 0, wph = 0;
       for (int it = 0; it < ((p.debug & 128) ? 0 : my_items); ++it) {
-        int b, cell0;
-        item_of(it, b, cell0);
+        int b, cell0, x0, x1;
+        item_of(it, b, cell0, x0, x1);
         const int64_t q0 = (int64_t)b * p.ls.frame_pitch + p.ls.guard + cell0;
-        for (int x = 0; x < S; ++x) {
+        const int xa = x0 > 0 ? x0 - 1 : 0, xb = x1 < S ? x1 : S - 1;
+        for (int x = xa; x <= xb; ++x) {
           mbar_wait(BAR(B_WIN_EMPTY + ws), wph ^ 1);
           if (p.debug & 4) { mbar_arrive(BAR(B_WIN_FULL + ws)); if (++ws == p.stages) { ws = 0; wph ^= 1; } continue; }
           mbar_expect_tx(BAR(B_WIN_FULL + ws), p.stage_bytes);
@@ -176,62 +189,66 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
     mbar_wait_warp(BAR(B_W_FULL), 0);
     int ws = 0;
     uint32_t wph = 0;
-    uint32_t slot = 0, use_par = 0;            // ring slot of the current plane's own output and the parity of its use count
+    uint32_t G = G_START;                        // outputs opened before this item
+    auto SLOT = [&](uint32_t g) { return g % (uint32_t)NS; };
+    auto PAR = [&](uint32_t g) { return (g / (uint32_t)NS) & 1u; };
     for (int it = 0; it < my_items; ++it) {
-      for (int x = 0; x < S; ++x) {
-        const uint32_t slot_n = slot + 1 == (uint32_t)NS ? 0u : slot + 1;       // output x+1
-        const uint32_t par_n = slot + 1 == (uint32_t)NS ? use_par ^ 1u : use_par;
-        const uint32_t slot_p = slot == 0 ? (uint32_t)NS - 1 : slot - 1;          // output x-1
-        // slots this plane opens: output x+1, and output 0 with the first plane
+      int b_, cell0_, x0, x1;
+      item_of(it, b_, cell0_, x0, x1);
+      const int xa = x0 > 0 ? x0 - 1 : 0, xb = x1 < S ? x1 : S - 1;
+      for (int xi = xa; xi <= xb; ++xi) {
+        // band: row block j of the weight array feeds output xi - 1 + j, kept to the outputs of this march
+        const int j_lo = xi - 1 >= x0 ? 0 : (xi >= x0 ? 1 : 2);
+        const int j_hi = xi + 1 < x1 ? 2 : (xi < x1 ? 1 : 0);
+        const int jf = (xi == xa && xa == x0) ? 1 : 2;          // first block this plane OPENS (overwrites)
+        const uint32_t gj0 = G + (uint32_t)(xi - x0) - 1u;      // running index of block 0's output
         if (!(p.debug & 16)) {
-          if (x == 0) mbar_wait_warp(BAR(B_ACC_EMPTY + (int)slot), use_par ^ 1u);
-          if (x + 1 < S) mbar_wait_warp(BAR(B_ACC_EMPTY + (int)slot_n), par_n ^ 1u);
+          for (int j = jf > j_lo ? jf : j_lo; j <= j_hi; ++j)
+            mbar_wait_warp(BAR(B_ACC_EMPTY + (int)SLOT(gj0 + (uint32_t)j)), PAR(gj0 + (uint32_t)j) ^ 1u);
         }
         if (!(p.debug & 32)) mbar_wait_warp(BAR(B_WIN_FULL + ws), wph);
         tc_fence_after();
         const uint32_t stage = win0 + (uint32_t)ws * stage16;
         const uint32_t a0 = stage | a_lbo;
         if (leader && !no_mma) {
-          // band: row block j of the weight array feeds output x - 1 + j (slots slot_p, slot, slot_n)
-          const uint32_t dp = tmem_u + slot_p * N0, dc = tmem_u + slot * N0, dn = tmem_u + slot_n * N0;
-          if (x == 0) {                                   // outputs 0 and 1, both opened here
-            if (slot_n != 0) RUN(a0, w_b + N0, dc, ID2, 0u, false);
-            else { RUN(a0, w_b + N0, dc, ID1, 0u, false); RUN(a0, w_b + 2 * N0, dn, ID1, 0u, false); }
-          } else if (x + 1 == S) {                        // outputs S-2 and S-1, both open
-            if (slot != 0) RUN(a0, w_b, dp, ID2, 1u, false);
-            else { RUN(a0, w_b, dp, ID1, 1u, false); RUN(a0, w_b + N0, dc, ID1, 1u, false); }
-          } else if (slot != 0 && slot_n != 0) {          // the common case: three consecutive slots
-            // first MMA split: accumulate into the two open outputs, overwrite the slot this plane opens
-            tc_mma_bf16(dp, DESC(a0), DESC(w_b), ID2, 1u);
-            tc_mma_bf16(dn, DESC(a0), DESC(w_b + 2 * N0), ID1, 0u);
-            RUN(a0, w_b, dp, ID3, 1u, true);
-          } else if (slot == 0) {                         // ring wraps after output x-1
-            RUN(a0, w_b, dp, ID1, 1u, false);
-            tc_mma_bf16(dc, DESC(a0), DESC(w_b + N0), ID1, 1u);
-            tc_mma_bf16(dn, DESC(a0), DESC(w_b + 2 * N0), ID1, 0u);
-            RUN(a0, w_b + N0, dc, ID2, 1u, true);
-          } else {                                        // ring wraps after output x
-            RUN(a0, w_b, dp, ID2, 1u, false);
-            RUN(a0, w_b + 2 * N0, dn, ID1, 0u, false);
-          }
+          // consecutive ring slots: run A up to the end of the ring, run B from slot 0
+          const int nb = j_hi - j_lo + 1;
+          const uint32_t sA = SLOT(gj0 + (uint32_t)j_lo);
+          const int nA = nb < NS - (int)sA ? nb : NS - (int)sA, nB = nb - nA;
+          const uint32_t dA = tmem_u + sA * N0, dB = tmem_u;
+          const uint32_t bA = w_b + (uint32_t)(j_lo * N0), bB = w_b + (uint32_t)((j_lo + nA) * N0);
+          auto IDN = [&](int n) { return ID1 + (uint32_t)(n - 1) * ((uint32_t)(N0 >> 3) << 17); };
+          // first MMA of the plane, split so that opened slots are overwritten and open ones accumulated
+          auto FIRST = [&](int ja, int n, uint32_t d, uint32_t bb) {
+            int na = jf - ja; na = na < 0 ? 0 : (na > n ? n : na);
+            if (na > 0) tc_mma_bf16(d, DESC(a0), DESC(bb), IDN(na), 1u);
+            if (n - na > 0) tc_mma_bf16(d + (uint32_t)(na * N0), DESC(a0), DESC(bb + (uint32_t)(na * N0)), IDN(n - na), 0u);
+          };
+          FIRST(j_lo, nA, dA, bA);
+          if (nB > 0) FIRST(j_lo + nA, nB, dB, bB);
+          RUN(a0, bA, dA, IDN(nA), 1u, true);
+          if (nB > 0) RUN(a0, bB, dB, IDN(nB), 1u, true);
           if constexpr (KSTEPS2 > 0) {
             // fused 1x1 shortcut: the plane's own output, from the halo-free window of the second source
-            const uint32_t a2 = (stage + (uint32_t)(2 * KSTEPS) * (p.win_bytes >> 4)) | a2_lbo;
+            if (xi >= x0 && xi < x1) {
+              const uint32_t a2 = (stage + (uint32_t)(2 * KSTEPS) * (p.win_bytes >> 4)) | a2_lbo;
+              const uint32_t dc = tmem_u + SLOT(gj0 + 1u) * N0;
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS2; ++ks)
-              tc_mma_bf16(dc, DESC(a2 + (uint32_t)ks * a2_ks_step), DESC(w2_b + (uint32_t)ks * b2_ks_step), ID1, 1u);
+              for (int ks = 0; ks < KSTEPS2; ++ks)
+                tc_mma_bf16(dc, DESC(a2 + (uint32_t)ks * a2_ks_step), DESC(w2_b + (uint32_t)ks * b2_ks_step), ID1, 1u);
+            }
           }
         }
         if (leader) {
           if (!(p.debug & 128)) tc_commit(BAR(B_WIN_EMPTY + ws));
           if (!(p.debug & 64)) {
-            if (x > 0) tc_commit(BAR(B_ACC_FULL + (int)slot_p));          // output x-1 is complete
-            if (x + 1 == S) tc_commit(BAR(B_ACC_FULL + (int)slot));       // so is the last one
+            if (j_lo == 0) tc_commit(BAR(B_ACC_FULL + (int)SLOT(gj0)));                             // output xi-1 is complete
+            if (xi == xb && j_lo <= 1 && j_hi >= 1) tc_commit(BAR(B_ACC_FULL + (int)SLOT(gj0 + 1u)));  // so is the last one
           }
         }
         if (++ws == p.stages) { ws = 0; wph ^= 1u; }
-        slot = slot_n; use_par = par_n;
       }
+      G += (uint32_t)(x1 - x0);
     }
     if (p.debug & (64 | 128)) {                  // tuning only: nobody else waits for the MMAs, so drain them here
       if (leader) tc_commit(BAR(B_W_FULL));
@@ -247,10 +264,10 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
     float bs[N0];
 #pragma unroll
     for (int j = 0; j < N0; ++j) bs[j] = s_bias[j];
-    uint32_t G = 0;
+    uint32_t G = G_START;
     for (int it = 0; it < ((p.debug & 64) ? 0 : my_items); ++it) {
-      int b, cell0;
-      item_of(it, b, cell0);
+      int b, cell0, x0, x1;
+      item_of(it, b, cell0, x0, x1);
       const int cell = cell0 + quarter * 32 + lane;
       const int y = (int)fdiv((uint32_t)cell, p.fd_py);
       const int z = cell - y * p.ls.pitch_y;
@@ -261,14 +278,14 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
 #pragma unroll
         for (int g = 0; g < 2 * NCH; ++g) {
           rn[g] = make_uint4(0, 0, 0, 0);
-          if (has_res && valid && x < S && !(p.debug & 2))
+          if (has_res && valid && x < x1 && !(p.debug & 2))
             rn[g] = *reinterpret_cast<const uint4*>(p.res + ((int64_t)g * p.ld.plane_stride + dpos0 + (int64_t)x * p.ld.pitch_x) * 8);
         }
       };
-      int x = HALVES == 2 ? (int)((G & 1u) ^ half) : 0;   // this warp's planes: global output counter parity == half
+      int x = x0 + (HALVES == 2 ? (int)((G & 1u) ^ half) : 0);   // this warp's planes: running output counter parity == half
       load_res(x);
-      for (; x < S; x += HALVES) {
-        const uint32_t gp = G + (uint32_t)x;
+      for (; x < x1; x += HALVES) {
+        const uint32_t gp = G + (uint32_t)(x - x0);
         const int slot = (int)(gp % (uint32_t)NS);
         uint4 rc[2 * NCH];
 #pragma unroll
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
           }
         }
       }
-      G += (uint32_t)S;
+      G += (uint32_t)(x1 - x0);
     }
   }
   tc_fence_before();
@@ -396,8 +413,12 @@ int launch_conv_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const
       if (n_configured < 16) configured[n_configured++] = fn;
     }
   }
+  // CTAs take equal contiguous ranges of (item, plane) pairs; at least 16 planes each so that the one or two
+  // extra input planes at the ends of a partial march stay a small fraction
   const int slots = kNumSMs * (two ? 2 : 1);
-  const int grid = p.n_items < slots ? p.n_items : slots;
+  int grid = (int)(((int64_t)p.n_items * S + 15) / 16);
+  if (grid > slots) grid = slots;
+  if (grid < 1) grid = 1;
   fn<<<grid, march_threads(two), (size_t)p.off_bar + 1024, st>>>(p);
   SE_CUDA_LAUNCH_CHECK("conv_march");
   return SCENEEGO_OK;

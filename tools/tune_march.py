@@ -42,8 +42,7 @@ if __name__ == "__main__":
     for cin, res in ((32, True), (32, False), (16, False)):
         us, tf = time_layer(cin, 64, B, res, False, {})
         print(f"conv_tc   {cin}->32 res={int(res)}                         {us:7.1f} us/frame {tf:6.0f} TF", flush=True)
-        envs = [{"SCENEEGO_MARCH_CTAS": "1"}, {}, {"SCENEEGO_MARCH_STAGES": "2"}, {"SCENEEGO_MARCH_DEBUG": "14"},
-                {"SCENEEGO_MARCH_DEBUG": "240"}, {"SCENEEGO_MARCH_DEBUG": "15"}]
+        envs = [{}, {"SCENEEGO_MARCH_CTAS": "1"}, {"SCENEEGO_MARCH_DEBUG": "14"}]
         for env in envs:
             us, tf = time_layer(cin, 64, B, res, True, env)
             print(f"march     {cin}->32 res={int(res)} {str(env):36s} {us:7.1f} us/frame {tf:6.0f} TF", flush=True)
