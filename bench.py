@@ -257,20 +257,22 @@ def ours_arm(args):
         conv_ms = kern["v2v"]["conv_ms_per_frame"]
         conv_fl = kern["v2v"]["conv_flops_per_frame"]
         ach = conv_fl / (conv_ms * 1e-3) / 1e12
-        # dominant kernel: the nine 3^3 Conv3d(32,32) launches at 64^3 (conv_tc_kernel<2,4,2,3,2>, CTA pairs) --
-        # the largest share of the step (profiles/r01_ncu_launch_shares_final.txt); the stem and the
-        # whole tensor path are reported next to it
+        # dominant kernel family: the nine 3^3 Conv3d(32,32) launches at 64^3 (conv_march_kernel, csrc/march.cu) --
+        # the largest share of the step together with the stem (profiles/r01_ncu_launch_shares_march.txt); the
+        # stem and the whole tensor path are reported next to it
         fam = kern["v2v"]["families"]
         c32 = fam["conv3_32_32_full_res"]
         n_launch_frames = kern["v2v"]["chunk_frames"]
-        roof = {"kernel": "conv_tc_kernel<2,4,2,3,2> (tcgen05 cta_group::2 implicit-GEMM Conv3d 3x3x3 32->32 at 64^3; "
-                          f"{c32['launches']} launches per {n_launch_frames}-frame chunk)",
+        roof = {"kernel": "conv_march_kernel<2,*,2,1> (tcgen05 x-marching banded implicit-GEMM Conv3d 3x3x3 32->32 at 64^3, "
+                          f"N=96 MMAs into a ring of TMEM slots, resident weights; {c32['launches']} launches per "
+                          f"{n_launch_frames}-frame chunk)",
                 "bound": "tensor", "achieved": c32["tflops"], "peak": tc_peak, "unit": "TFLOP/s",
                 "frac": c32["tflops"] / tc_peak,
-                "traffic": 516.7e6,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture "
-                                "at 16 frames per launch (profiles/r01_ncu_conv_tc_final.txt): 282 MB + 235 MB vs "
-                                "563 MB algorithmic (2 x 16 x 17.6 MB)",
+                "traffic": 788.0e6,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture at "
+                                "16 frames per launch (profiles/r01_ncu_conv_march.txt), mean of a launch without residual "
+                                "(387 + 242 MB vs 563 MB algorithmic = 2 x 16 x 17.6 MB) and one with (696 + 251 MB vs 845 MB): "
+                                "the halo cells shared by neighbouring 128-cell tiles hit L2 only partly",
                 "peak_source": peak_src,
                 "how": f"algorithmic 2*32*32*27*64^3 = 14.50 GFLOP per frame x {n_launch_frames} frames per launch / mean "
                        "CUDA-event duration of those launches on the launching stream (sceneego_v2v_run_profile)",

@@ -17,8 +17,14 @@
 //     the first MMA of a plane is split so that the newly opened slot is overwritten, not accumulated.
 //   warp 0 = producer (cp.async.bulk of one (cin/8)-plane window per input plane, 2..8-stage ring)
 //   warp 1 = TMEM allocator + the one MMA issuer (an N = 96 MMA takes longer than the 41.5-cycle issue floor)
-//   warps 2-9 = epilogue: two warps per TMEM lane quarter, alternating output planes; row decode (y, z, validity)
-//               is done once per item because it is the same for every plane of the march.
+//   then 4 or 8 epilogue warps: one or two per TMEM lane quarter (two alternate output planes); row decode
+//   (y, z, validity) is done once per item because it is the same for every plane of the march.
+// Measured (tools/mma_band.cu, tools/tune_march.py, profiles/r01_mma_band.txt, r01_tune_march.txt): the band MMAs
+// cost what the model says (N = 96: 56.1 cycles at any column / row offset; 58.5 with the split first MMA and the
+// commits), but the issuing warp's per-plane bookkeeping (~300-600 cycles of waits, commits and ring arithmetic
+// executed by ONE warp) is NOT hidden behind the tensor pipe's short queue.  Hence two CTAs per SM, each with
+// half of tensor memory (ring of 8 slots) -- one CTA's bookkeeping overlaps the other's MMAs: 15.7 -> 12.4 us per
+// 32->32 layer and frame (conv_tc with CTA pairs: 15.3), tensor-only floor 9.9 us.
 // The fused 1x1 projection shortcut (Res3DBlock.skip_con) is one extra N = Cout MMA per plane on the plane's
 // own slot, from a halo-free window of the second source staged with the plane.
 #include "tc_common.cuh"
@@ -50,7 +56,6 @@ struct MarchParams {
   int tiles_per_plane, n_items;
   int halo;
   int stages;
-  int debug;                   // tuning switches (SCENEEGO_MARCH_DEBUG), 0 in production
   uint32_t win_bytes, win2_bytes, stage_bytes;
   uint32_t w_bytes, w2_bytes;
   uint32_t off_win, off_bias, off_bar;   // weights live at offset 0
@@ -92,22 +97,33 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
 
-  // Work split: the (item, plane) pairs, item-major, are cut into gridDim.x equal contiguous ranges, so a CTA
-  // marches over [x0, x1) of its first and last item and over all of the others: the load is balanced to one
-  // plane whatever the item count (2112 items on 296 CTAs would otherwise leave 12 % of the machine idle).
-  // A march over [x0, x1) reads input planes max(x0-1, 0) .. min(x1, S-1).
-  const uint32_t total = (uint32_t)p.n_items * (uint32_t)S;
-  const uint32_t base = total / gridDim.x, rem = total % gridDim.x;
-  const uint32_t P0 = blockIdx.x * base + (blockIdx.x < rem ? blockIdx.x : rem);
-  const uint32_t P1 = P0 + base + (blockIdx.x < rem ? 1u : 0u);
-  const uint32_t first_item = P1 > P0 ? P0 / (uint32_t)S : 0u, last_item = P1 > P0 ? (P1 - 1) / (uint32_t)S : 0u;
-  const int my_items = P1 > P0 ? (int)(last_item - first_item + 1) : 0;
+  // Work split.  Whole rounds: CTA k marches items k, k + grid, ... -- neighbouring CTAs work on neighbouring
+  // tiles of the same frame at the same plane at the same time, so the halo cells two tiles share are read from
+  // DRAM once and hit in L2 for the other (with contiguous item ranges per CTA ncu showed a 2 % L2 hit rate and
+  // 2.05x the compulsory DRAM reads).  The items of the last, incomplete round (2112 items on 296 CTAs would
+  // leave 12 % of the machine idle) are cut by PLANES into gridDim.x equal ranges: a march over [x0, x1) reads
+  // input planes max(x0-1, 0) .. min(x1, S-1).
+  const uint32_t n_whole = (uint32_t)p.n_items / gridDim.x;                       // rounds of whole items
+  const uint32_t left_items = (uint32_t)p.n_items - n_whole * gridDim.x;
+  const uint32_t left_total = left_items * (uint32_t)S;                           // < gridDim.x * S
+  const uint32_t lbase = left_total / gridDim.x, lrem = left_total % gridDim.x;
+  const uint32_t Q0 = blockIdx.x * lbase + (blockIdx.x < lrem ? blockIdx.x : lrem);
+  const uint32_t Q1 = Q0 + lbase + (blockIdx.x < lrem ? 1u : 0u);
+  const uint32_t lfirst = Q1 > Q0 ? Q0 / (uint32_t)S : 0u, llast = Q1 > Q0 ? (Q1 - 1) / (uint32_t)S : 0u;
+  const int my_items = (int)n_whole + (Q1 > Q0 ? (int)(llast - lfirst + 1) : 0);
   auto item_of = [&](int it, int& b, int& cell0, int& x0, int& x1) {
-    const uint32_t item = first_item + (uint32_t)it;
+    uint32_t item;
+    if ((uint32_t)it < n_whole) {
+      item = blockIdx.x + (uint32_t)it * gridDim.x;
+      x0 = 0; x1 = S;
+    } else {
+      const uint32_t li = lfirst + ((uint32_t)it - n_whole);
+      item = n_whole * gridDim.x + li;
+      x0 = li == lfirst ? (int)(Q0 - lfirst * (uint32_t)S) : 0;
+      x1 = li == llast ? (int)(Q1 - llast * (uint32_t)S) : S;
+    }
     b = (int)fdiv(item, p.fd_tpp);
     cell0 = (int)(item - (uint32_t)b * (uint32_t)p.tiles_per_plane) * MARCH_L;
-    x0 = it == 0 ? (int)(P0 - first_item * (uint32_t)S) : 0;
-    x1 = item == last_item ? (int)(P1 - last_item * (uint32_t)S) : S;
   };
   constexpr uint32_t G_START = 4u * NS;   // running output counter; the offset keeps (G - 2) non-negative, slot 0 / parity 0
 
@@ -121,14 +137,13 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
         bulk_g2s(sbase + o, reinterpret_cast<const char*>(p.w) + o, n, BAR(B_W_FULL));
       }
       int ws = 0, wph = 0;
-      for (int it = 0; it < ((p.debug & 128) ? 0 : my_items); ++it) {
+      for (int it = 0; it < my_items; ++it) {
         int b, cell0, x0, x1;
         item_of(it, b, cell0, x0, x1);
         const int64_t q0 = (int64_t)b * p.ls.frame_pitch + p.ls.guard + cell0;
         const int xa = x0 > 0 ? x0 - 1 : 0, xb = x1 < S ? x1 : S - 1;
         for (int x = xa; x <= xb; ++x) {
           mbar_wait(BAR(B_WIN_EMPTY + ws), wph ^ 1);
-          if (p.debug & 4) { mbar_arrive(BAR(B_WIN_FULL + ws)); if (++ws == p.stages) { ws = 0; wph ^= 1; } continue; }
           mbar_expect_tx(BAR(B_WIN_FULL + ws), p.stage_bytes);
           const int64_t qc = q0 + (int64_t)x * p.ls.pitch_x;
           const uint32_t dst0 = sbase + p.off_win + (uint32_t)ws * p.stage_bytes;
@@ -168,7 +183,6 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
     const uint32_t pitch_y = (uint32_t)p.ls.pitch_y;
     const uint32_t win0 = ((sbase + p.off_win) >> 4) & 0x3FFFu;                  // stage 0, in 16-B units
     const uint32_t stage16 = p.stage_bytes >> 4;
-    const bool no_mma = (p.debug & 1) != 0;
     // all (dy,dz,k-step) MMAs of one run of the band: B rows from block ja on, N = idesc's, into column d
     auto RUN = [&](uint32_t a0, uint32_t bb, uint32_t d, uint32_t idesc, uint32_t acc_first, bool skip_first) {
 #pragma unroll
@@ -202,15 +216,13 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
         const int j_hi = xi + 1 < x1 ? 2 : (xi < x1 ? 1 : 0);
         const int jf = (xi == xa && xa == x0) ? 1 : 2;          // first block this plane OPENS (overwrites)
         const uint32_t gj0 = G + (uint32_t)(xi - x0) - 1u;      // running index of block 0's output
-        if (!(p.debug & 16)) {
-          for (int j = jf > j_lo ? jf : j_lo; j <= j_hi; ++j)
-            mbar_wait_warp(BAR(B_ACC_EMPTY + (int)SLOT(gj0 + (uint32_t)j)), PAR(gj0 + (uint32_t)j) ^ 1u);
-        }
-        if (!(p.debug & 32)) mbar_wait_warp(BAR(B_WIN_FULL + ws), wph);
+        for (int j = jf > j_lo ? jf : j_lo; j <= j_hi; ++j)      // the epilogue has drained the slots this plane opens
+          mbar_wait_warp(BAR(B_ACC_EMPTY + (int)SLOT(gj0 + (uint32_t)j)), PAR(gj0 + (uint32_t)j) ^ 1u);
+        mbar_wait_warp(BAR(B_WIN_FULL + ws), wph);
         tc_fence_after();
         const uint32_t stage = win0 + (uint32_t)ws * stage16;
         const uint32_t a0 = stage | a_lbo;
-        if (leader && !no_mma) {
+        if (leader) {
           // consecutive ring slots: run A up to the end of the ring, run B from slot 0
           const int nb = j_hi - j_lo + 1;
           const uint32_t sA = SLOT(gj0 + (uint32_t)j_lo);
@@ -240,19 +252,13 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
           }
         }
         if (leader) {
-          if (!(p.debug & 128)) tc_commit(BAR(B_WIN_EMPTY + ws));
-          if (!(p.debug & 64)) {
-            if (j_lo == 0) tc_commit(BAR(B_ACC_FULL + (int)SLOT(gj0)));                             // output xi-1 is complete
-            if (xi == xb && j_lo <= 1 && j_hi >= 1) tc_commit(BAR(B_ACC_FULL + (int)SLOT(gj0 + 1u)));  // so is the last one
-          }
+          tc_commit(BAR(B_WIN_EMPTY + ws));
+          if (j_lo == 0) tc_commit(BAR(B_ACC_FULL + (int)SLOT(gj0)));                             // output xi-1 is complete
+          if (xi == xb && j_lo <= 1 && j_hi >= 1) tc_commit(BAR(B_ACC_FULL + (int)SLOT(gj0 + 1u)));  // so is the last one
         }
         if (++ws == p.stages) { ws = 0; wph ^= 1u; }
       }
       G += (uint32_t)(x1 - x0);
-    }
-    if (p.debug & (64 | 128)) {                  // tuning only: nobody else waits for the MMAs, so drain them here
-      if (leader) tc_commit(BAR(B_W_FULL));
-      mbar_wait_warp(BAR(B_W_FULL), 1);
     }
     __syncwarp();
   } else {
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
 #pragma unroll
     for (int j = 0; j < N0; ++j) bs[j] = s_bias[j];
     uint32_t G = G_START;
-    for (int it = 0; it < ((p.debug & 64) ? 0 : my_items); ++it) {
+    for (int it = 0; it < my_items; ++it) {
       int b, cell0, x0, x1;
       item_of(it, b, cell0, x0, x1);
       const int cell = cell0 + quarter * 32 + lane;
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
 #pragma unroll
         for (int g = 0; g < 2 * NCH; ++g) {
           rn[g] = make_uint4(0, 0, 0, 0);
-          if (has_res && valid && x < x1 && !(p.debug & 2))
+          if (has_res && valid && x < x1)
             rn[g] = *reinterpret_cast<const uint4*>(p.res + ((int64_t)g * p.ld.plane_stride + dpos0 + (int64_t)x * p.ld.pitch_x) * 8);
         }
       };
@@ -295,15 +301,13 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
         tc_fence_after();
         uint32_t raw[NCH][16];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)slot * N0;
-        if (!(p.debug & 8)) {
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) tc_ld16(taddr + (uint32_t)(16 * c), raw[c]);
-          tc_wait_ld();
-        }
+        for (int c = 0; c < NCH; ++c) tc_ld16(taddr + (uint32_t)(16 * c), raw[c]);
+        tc_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + slot));
-        if (valid && !(p.debug & 2)) {
+        if (valid) {
           const int64_t dpos = dpos0 + (int64_t)x * p.ld.pitch_x;
 #pragma unroll
           for (int g = 0; g < 2 * NCH; ++g) {
@@ -392,7 +396,6 @@ int launch_conv_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const
   if (stages > MARCH_MAX_STAGES) stages = MARCH_MAX_STAGES;
   { const char* e = getenv("SCENEEGO_MARCH_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages) stages = atoi(e); }
   p.stages = stages;
-  { const char* e = getenv("SCENEEGO_MARCH_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.off_win = p.w_bytes + p.w2_bytes;
   p.off_bias = p.off_win + (uint32_t)stages * p.stage_bytes;
   p.off_bar = p.off_bias + 512;

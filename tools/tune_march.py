@@ -9,7 +9,7 @@ from sceneego_b200 import _lib
 
 
 def time_layer(cin, S, B, res, march, env, reps=5, xs=2, pair=2):
-    for k in ("SCENEEGO_MARCH_DEBUG", "SCENEEGO_MARCH_STAGES", "SCENEEGO_MARCH_CTAS"):
+    for k in ("SCENEEGO_MARCH_STAGES", "SCENEEGO_MARCH_CTAS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     torch.manual_seed(0)
@@ -42,7 +42,7 @@ if __name__ == "__main__":
     for cin, res in ((32, True), (32, False), (16, False)):
         us, tf = time_layer(cin, 64, B, res, False, {})
         print(f"conv_tc   {cin}->32 res={int(res)}                         {us:7.1f} us/frame {tf:6.0f} TF", flush=True)
-        envs = [{}, {"SCENEEGO_MARCH_CTAS": "1"}, {"SCENEEGO_MARCH_DEBUG": "14"}]
+        envs = [{}, {"SCENEEGO_MARCH_CTAS": "1"}, {"SCENEEGO_MARCH_STAGES": "2"}]
         for env in envs:
             us, tf = time_layer(cin, 64, B, res, True, env)
             print(f"march     {cin}->32 res={int(res)} {str(env):36s} {us:7.1f} us/frame {tf:6.0f} TF", flush=True)
