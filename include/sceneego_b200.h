@@ -154,6 +154,18 @@ int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int h, int w, c
                                 float* d_occ_f32, void* d_occ_bf16, const sceneego_vol_layout_t* lay,
                                 int channel, void* stream);
 
+/* Same, with the DATASET's preprocessing of the raw depth map fused into the load:
+ * replaces cv2.resize(depth, (pre_w, pre_h), INTER_NEAREST) when the raw map is not pre_h x pre_w, and
+ * depth_map[depth_map > clamp_max] = clamp_max (dataset/demo_dataset.py:86-91, dataset/test_dataset.py:138-143),
+ * followed by sceneego_voxelize_depth_f64 on the result; with d_occ_f32 it is also the voxel_output=True path
+ * depth_map_to_voxel (dataset/real_depth_utils.py:29-60).  Nearest indices are OpenCV's:
+ * min(cvFloor(dst * (1. / ((double)n_dst / n_src))), n_src - 1).  clamp_max = +inf disables the clamp.
+ *   d_depth_raw (B,h,w) f32 as decoded from the EXR (first channel) */
+int sceneego_voxelize_depth_raw_f64(const float* d_depth_raw, int batch, int h, int w, int pre_h, int pre_w,
+                                    float clamp_max, const double* d_ray, int img_h, int img_w, int volume_size,
+                                    double cuboid_side, float* d_occ_f32, void* d_occ_bf16,
+                                    const sceneego_vol_layout_t* lay, int channel, void* stream);
+
 /* Conversions between (B,C,S,S,S) f32 NCDHW and planar padded bf16 (for the
  * scene_volumes= input path, voxel_net_depth.py:246-249, and for tests). */
 int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,

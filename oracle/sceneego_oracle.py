@@ -172,12 +172,30 @@ def unproject(features: torch.Tensor, grid_batch: torch.Tensor, volume_size: int
 # ----------------------------------------------------------------------------
 # a5: depth map -> occupancy grid
 # ----------------------------------------------------------------------------
+def nearest_index(n_src: int, n_dst: int) -> np.ndarray:
+    """Index map of cv2.resize(..., INTER_NEAREST) (OpenCV resizeNN): src = min(cvFloor(dst * ifx), n_src - 1)
+    with ifx = 1. / ((double)n_dst / n_src) in fp64 -- pinned against cv2 itself for 3500 size pairs by
+    tests/make_golden.py (tests/golden/nearest_index.npz); floor(dst * n_src / n_dst) in exact arithmetic is
+    NOT the same map (115 source sizes below 1400 differ)."""
+    ifx = 1.0 / (float(n_dst) / float(n_src))
+    return np.minimum(np.floor(np.arange(n_dst, dtype=np.float64) * ifx).astype(np.int64), n_src - 1)
+
+
 def resize_nearest(depth: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """cv2.resize(..., INTER_NEAREST): src = min(floor(dst * in/out), in-1)."""
+    """cv2.resize(depth, (out_w, out_h), interpolation=cv2.INTER_NEAREST)."""
     h, w = depth.shape
-    sy = np.minimum(np.floor(np.arange(out_h) * (h / out_h)).astype(np.int64), h - 1)
-    sx = np.minimum(np.floor(np.arange(out_w) * (w / out_w)).astype(np.int64), w - 1)
-    return depth[sy][:, sx]
+    return depth[nearest_index(h, out_h)][:, nearest_index(w, out_w)]
+
+
+def preprocess_depth(depth_raw: np.ndarray, pre_h: int = 1024, pre_w: int = 1280, clamp_max: float = 10.0) -> np.ndarray:
+    """dataset/demo_dataset.py:86-91 (= dataset/test_dataset.py:138-143): nearest resize to 1280 x 1024 when the
+    decoded map has another size, then depth_map[depth_map > 10] = 10."""
+    d = np.asarray(depth_raw, dtype=np.float32)
+    if d.shape[0] != pre_h or d.shape[1] != pre_w:
+        d = resize_nearest(d, pre_h, pre_w)
+    d = d.copy()
+    d[d > clamp_max] = clamp_max
+    return d
 
 
 def voxelize_depth(depth: np.ndarray, ray: np.ndarray, volume_size: int, cuboid_side: float,

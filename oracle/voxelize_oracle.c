@@ -47,8 +47,9 @@ long oracle_voxelize(const float* depth, int h, int w, const double* ray, int im
       float dv = 0.0f;
       const int xs = x - pad;
       if (xs >= 0 && xs < img_h) { /* cv2.resize INTER_NEAREST then np.pad */
-        int sy = (int)floor((double)y * ((double)h / img_h));
-        int sx = (int)floor((double)xs * ((double)w / img_h));
+        /* OpenCV resizeNN: cvFloor(dst * ifx), ifx = 1. / ((double)n_dst / n_src) */
+        int sy = (int)floor((double)y * (1.0 / ((double)img_h / (double)h)));
+        int sx = (int)floor((double)xs * (1.0 / ((double)img_h / (double)w)));
         if (sy > h - 1) sy = h - 1;
         if (sx > w - 1) sx = w - 1;
         dv = depth[(size_t)sy * w + sx];

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
-    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march",
+    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64",
 ]
 
 
@@ -211,6 +211,17 @@ def voxelize_depth(depth: torch.Tensor, ray: torch.Tensor, img_h: int, img_w: in
         _ptr(depth), b, h, w, _ptr(ray), int(img_h), int(img_w), int(volume_size), C.c_double(cuboid_side),
         _ptr(occ_f32), _ptr(occ_bf16), C.byref(lay) if lay is not None else None, int(channel), _stream()),
         "voxelize_depth")
+
+
+def voxelize_depth_raw(depth_raw: torch.Tensor, pre_hw, clamp_max: float, ray: torch.Tensor, img_h: int, img_w: int,
+                       volume_size: int, cuboid_side: float, occ_f32: Optional[torch.Tensor],
+                       occ_bf16: Optional[torch.Tensor], lay: Optional[VolLayout], channel: int = 0) -> None:
+    """Raw depth maps: the dataset's nearest resize to `pre_hw` and clamp fused into the voxelisation."""
+    b, h, w = depth_raw.shape
+    _check(load_library().sceneego_voxelize_depth_raw_f64(
+        _ptr(depth_raw), b, h, w, int(pre_hw[0]), int(pre_hw[1]), C.c_float(clamp_max), _ptr(ray), int(img_h), int(img_w),
+        int(volume_size), C.c_double(cuboid_side), _ptr(occ_f32), _ptr(occ_bf16),
+        C.byref(lay) if lay is not None else None, int(channel), _stream()), "voxelize_depth_raw")
 
 
 def pack_volume(x: torch.Tensor, out_bf16: torch.Tensor, lay: VolLayout, c_offset: int = 0) -> None:

@@ -321,8 +321,20 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
 // row-major, so depth, ray table (24 B / pixel, L2 resident across frames) and the
 // zero-padding test are all coalesced.  The scatter is a benign same-value race.
 // ---------------------------------------------------------------------------
+// Nearest-neighbour index maps exactly as OpenCV builds them (resizeNN): src = min(cvFloor(dst * ifx), n_src - 1)
+// with ifx = 1.0 / ((double)n_dst / n_src) evaluated in fp64 on the host -- NOT floor(dst * n_src / n_dst) in exact
+// arithmetic, which differs from cv2 for 115 source sizes below 1400 (e.g. 26 -> 1280).  Two maps are composed:
+// the model's resize to img_h x img_h (network/voxel_net_depth.py:197) after the dataset's optional resize of the
+// raw map to pre_h x pre_w (dataset/demo_dataset.py:86-88, dataset/test_dataset.py:138-140); identity when equal.
+struct NearestMaps {
+  double ify1, ifx1;   // img_h grid -> (pre_h, pre_w) grid
+  double ify0, ifx0;   // (pre_h, pre_w) grid -> raw (h, w) grid
+  int pre_h, pre_w;
+  float clamp_max;     // depth_map[depth_map > clamp_max] = clamp_max (demo_dataset.py:91); +inf = off
+};
+
 template <bool kPow2Side>
-__global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__ depth, int h, int w,
+__global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__ depth, int h, int w, NearestMaps nm,
                                                       const double* __restrict__ ray, int img_h, int img_w, int V,
                                                       double side, double inv_side, float* __restrict__ occ_f32,
                                                       __nv_bfloat16* __restrict__ occ_bf16,
@@ -333,9 +345,13 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
   const int xs = X - pad;
   const bool in_img = X < img_w;
   const bool in_src = in_img && xs >= 0 && xs < img_h;
-  // cv2.resize(INTER_NEAREST): src = min(floor(dst * in / out), in - 1)
-  int sy = (int)(((long long)Y * h) / img_h);
-  int sx = (int)(((long long)(in_src ? xs : 0) * w) / img_h);
+  // cv2.resize(INTER_NEAREST), model side then dataset side
+  int sy = (int)floor(__dmul_rn((double)Y, nm.ify1));
+  int sx = (int)floor(__dmul_rn((double)(in_src ? xs : 0), nm.ifx1));
+  sy = sy < nm.pre_h - 1 ? sy : nm.pre_h - 1;
+  sx = sx < nm.pre_w - 1 ? sx : nm.pre_w - 1;
+  sy = (int)floor(__dmul_rn((double)sy, nm.ify0));
+  sx = (int)floor(__dmul_rn((double)sx, nm.ifx0));
   sy = sy < h - 1 ? sy : h - 1;
   sx = sx < w - 1 ? sx : w - 1;
   // the pixel's ray is frame-invariant: fetched once for the `frames_per_block` frames this block covers
@@ -357,7 +373,10 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
     const int b = b_begin + f;
     if (b >= batch) break;                                  // uniform over the block
     float dv = 0.f;
-    if (in_src) dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
+    if (in_src) {
+      dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
+      dv = dv > nm.clamp_max ? nm.clamp_max : dv;             // NaN compares false and stays, like NumPy's mask
+    }
     int ix = -1, iy = 0, iz = 0;
     const bool zero = in_img && (dv == 0.0f);
     if (in_img && !zero) {
@@ -527,28 +546,50 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
   return SCENEEGO_OK;
 }
 
-extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int h, int w, const double* d_ray,
-                                           int img_h, int img_w, int V, double side, float* d_occ_f32,
-                                           void* d_occ_bf16, const sceneego_vol_layout_t* lay, int channel,
-                                           void* stream) {
+static int voxelize_impl(const float* d_depth, int batch, int h, int w, int pre_h, int pre_w, float clamp_max,
+                         const double* d_ray, int img_h, int img_w, int V, double side, float* d_occ_f32,
+                         void* d_occ_bf16, const sceneego_vol_layout_t* lay, int channel, void* stream) {
   SE_REQUIRE(d_depth && d_ray && (d_occ_f32 || d_occ_bf16), "voxelize: null argument");
-  SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && img_w >= img_h, "voxelize: bad shape");
+  SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && pre_h > 0 && pre_w > 0 && img_w >= img_h, "voxelize: bad shape");
   SE_REQUIRE(!d_occ_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
   SE_REQUIRE(!d_occ_bf16 || !lay->s2d || channel % 8 == 0, "voxelize: s2d occupancy follows whole channel groups");
   // several frames per block so that a pixel's ray is fetched once for all of them (grid.z <= 65535 either way)
   const int fpb = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
   dim3 grid((img_w + 255) / 256, img_h, (batch + fpb - 1) / fpb);
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
+  NearestMaps nm;
+  // OpenCV: inv_scale = (double)dsize / ssize; ifx = 1. / inv_scale
+  nm.ify1 = 1.0 / ((double)img_h / (double)pre_h);
+  nm.ifx1 = 1.0 / ((double)img_h / (double)pre_w);
+  nm.ify0 = (h == pre_h && w == pre_w) ? 1.0 : 1.0 / ((double)pre_h / (double)h);
+  nm.ifx0 = (h == pre_h && w == pre_w) ? 1.0 : 1.0 / ((double)pre_w / (double)w);
+  nm.pre_h = pre_h; nm.pre_w = pre_w; nm.clamp_max = clamp_max;
   int e2 = 0;
   const bool pow2 = side > 0 && frexp(side, &e2) == 0.5;       // side == 2^(e2-1): divide == exact multiply
   if (pow2)
-    voxelize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, 1.0 / side,
+    voxelize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 1.0 / side,
                                                                   d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb);
   else
-    voxelize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, d_ray, img_h, img_w, V, side, 0.0,
+    voxelize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 0.0,
                                                                    d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb);
   SE_CUDA_LAUNCH_CHECK("voxelize");
   return SCENEEGO_OK;
+}
+
+extern "C" int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int h, int w, const double* d_ray,
+                                           int img_h, int img_w, int V, double side, float* d_occ_f32,
+                                           void* d_occ_bf16, const sceneego_vol_layout_t* lay, int channel,
+                                           void* stream) {
+  return voxelize_impl(d_depth, batch, h, w, h, w, INFINITY, d_ray, img_h, img_w, V, side, d_occ_f32, d_occ_bf16, lay,
+                       channel, stream);
+}
+
+extern "C" int sceneego_voxelize_depth_raw_f64(const float* d_depth_raw, int batch, int h, int w, int pre_h, int pre_w,
+                                               float clamp_max, const double* d_ray, int img_h, int img_w, int V,
+                                               double side, float* d_occ_f32, void* d_occ_bf16,
+                                               const sceneego_vol_layout_t* lay, int channel, void* stream) {
+  return voxelize_impl(d_depth_raw, batch, h, w, pre_h, pre_w, clamp_max, d_ray, img_h, img_w, V, side, d_occ_f32,
+                       d_occ_bf16, lay, channel, stream);
 }
 
 extern "C" int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,

@@ -118,6 +118,10 @@ class VoxelNetwork_depth(nn.Module):
         self._axis = torch.stack([cv[:, 0, 0, 0], cv[0, :, 0, 1], cv[0, 0, :, 2]]).contiguous()
         self.last_launches = 0
         self._side_stream = None
+        # (pre_h, pre_w, clamp_max): depth_map_batch holds RAW decoded maps and the dataset's preprocessing
+        # (dataset/demo_dataset.py:86-91: nearest resize to 1280x1024, depth > 10 -> 10) is fused into the
+        # voxelisation kernel's load; None: the caller has preprocessed them, like the reference's datasets do
+        self.depth_preprocess = None
 
     def build_coord_volume(self):
         """network/voxel_net_depth.py:110-134, on the device (fp32, mul then add)."""
@@ -187,8 +191,14 @@ class VoxelNetwork_depth(nn.Module):
                 else:
                     d = depth_map_batch[s:s + n]
                     d = d.reshape(n, d.shape[-2], d.shape[-1]).contiguous().float()
-                    _lib.voxelize_depth(d, self._ray_dev, self.image_height, self.image_width, v,
-                                        float(self.cuboid_side), None, in_buf, pg.lay_in, channel=32)
+                    if self.depth_preprocess is not None:
+                        ph, pw, cm = self.depth_preprocess
+                        _lib.voxelize_depth_raw(d, (ph, pw), float(cm), self._ray_dev, self.image_height,
+                                                self.image_width, v, float(self.cuboid_side), None, in_buf, pg.lay_in,
+                                                channel=32)
+                    else:
+                        _lib.voxelize_depth(d, self._ray_dev, self.image_height, self.image_width, v,
+                                            float(self.cuboid_side), None, in_buf, pg.lay_in, channel=32)
                 launches += 1
             launches += vn.run_chunk(pg, n, logits[s:s + n])
         kp, volumes = _lib.softargmax3d(logits, float(self.volume_multiplier), bool(self.volume_softmax),

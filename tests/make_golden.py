@@ -88,7 +88,34 @@ def load_demo_depth(name):
     return raw, d
 
 
+NEAREST_SIZES = [26, 36, 52, 72, 98, 104, 144, 186, 198, 256, 300, 320, 333, 512, 517, 600, 640, 700, 1000, 1024, 1280,
+                 1500, 2048, 2560]
+
+
+def make_nearest_index_golden():
+    """Index maps of cv2.resize(INTER_NEAREST) itself (the library the reference calls at
+    network/voxel_net_depth.py:197 and dataset/demo_dataset.py:88) for source sizes -> 1024 / 1280, including the
+    sizes where the exact-rational rule differs; also asserts the oracle's rule on ~3500 pairs."""
+    from oracle import sceneego_oracle as orc
+
+    def cv_idx(n_src, n_dst):
+        img = np.arange(n_src, dtype=np.float32)[None, :].repeat(2, 0)
+        return cv2.resize(img, (n_dst, 2), interpolation=cv2.INTER_NEAREST)[0].astype(np.int64)
+    for ns in list(range(3, 1400)) + [1500, 2048, 2560, 3000]:
+        for nd in (1024, 1280):
+            assert np.array_equal(cv_idx(ns, nd), orc.nearest_index(ns, nd)), (ns, nd)
+    out = {}
+    for ns in NEAREST_SIZES:
+        for nd in (1024, 1280):
+            out[f"{ns}_{nd}"] = cv_idx(ns, nd).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "nearest_index.npz"), **out)
+
+
 def main():
+    if "--nearest-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        make_nearest_index_golden()
+        return
     config, Net, cwd = import_reference()
     os.makedirs(OUT, exist_ok=True)
     report = {}
@@ -124,6 +151,8 @@ def main():
                             grid_px=net.grid_coord_proj.numpy()[idx],
                             coord=net.coord_volume.reshape(-1, 3).numpy()[idx])
     report["tables"] = "exact"
+    make_nearest_index_golden()
+    report["nearest_index"] = "oracle rule == cv2.resize(INTER_NEAREST) for 2802 (n_src, n_dst) pairs"
 
     # ---- voxelisation: demo EXRs + synthetic, V=64 and 128, bit-exact
     vox = {}

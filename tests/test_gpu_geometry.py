@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from oracle import sceneego_oracle as orc
+from sceneego_b200 import _lib
 from sceneego_b200.utils import synth
 from tests import util
 
@@ -113,6 +114,47 @@ def test_voxelize_edge_cases_vs_oracle(cam, tables64):
     for side in (3.0, 1.7, 4.0):
         for d in (cases[3], cases[4]):
             assert np.array_equal(_voxelize(cam, d, 64, side)[0], orc.voxelize_depth(d, tables64.ray, 64, side)), side
+
+
+def test_voxelize_raw_depth_fused_preprocessing(cam, tables64):
+    """sceneego_voxelize_depth_raw_f64: the dataset's nearest resize to 1280x1024 and the 10 m clamp
+    (dataset/demo_dataset.py:86-91) fused into the voxelisation load.  Raw demo EXRs (512x640) against the
+    reference-generated occupancy; odd source sizes (where OpenCV's index map differs from the exact-rational one),
+    values above the clamp, NaN / Inf against the oracle."""
+    g = util.golden("voxel.npz")
+    ray = cam.ray_table_device(1280, 1024, "cuda")
+    for V in (64, 128):
+        raws = np.stack([g[f"{n}_raw"] for n in ("img_001000", "img_001796", "img_002376")])
+        occ = torch.zeros(3, V, V, V, device="cuda")
+        _lib.voxelize_depth_raw(torch.from_numpy(raws).cuda(), (1024, 1280), 10.0, ray, 1024, 1280, V, 2.0, occ, None, None)
+        for i, n in enumerate(("img_001000", "img_001796", "img_002376")):
+            assert np.array_equal(occ[i].cpu().numpy(), util.unpack_bits(g[f"{n}_v{V}"], V)), n
+    rng = np.random.default_rng(11)
+    for h, w in ((104, 144), (26, 36), (333, 517), (1024, 1280), (2048, 2560)):
+        raw = rng.random((2, h, w), dtype=np.float32) * 14 - 1          # above the clamp and below zero
+        raw[0, ::5, ::3] = np.nan
+        raw[1, ::7, ::2] = np.inf
+        occ = torch.zeros(2, 64, 64, 64, device="cuda")
+        _lib.voxelize_depth_raw(torch.from_numpy(raw).cuda(), (1024, 1280), 10.0, ray, 1024, 1280, 64, 2.0, occ, None, None)
+        for i in range(2):
+            ref = orc.voxelize_depth(orc.preprocess_depth(raw[i]), tables64.ray, 64, 2.0)
+            assert np.array_equal(occ[i].cpu().numpy(), ref), (h, w, i)
+    # the voxel_output=True dataset path (dataset/real_depth_utils.py:29-60) shares the kernel
+    from sceneego_b200.dataset import real_depth_utils as rdu
+    d = orc.preprocess_depth(g["img_001000_raw"])
+    vox = rdu.depth_map_to_voxel(tables64.ray, torch.from_numpy(d), 2.0, 64)          # reference-order NumPy ray table
+    assert np.array_equal(vox.cpu().numpy(), util.unpack_bits(g["img_001000_v64"], 64))
+    vox2 = rdu.depth_maps_to_voxels(ray, torch.from_numpy(g["img_001000_raw"][None]).cuda(), 2.0, 64)
+    assert torch.equal(vox2[0], vox)
+
+
+def test_voxelize_odd_source_size_matches_cv2_rule(cam, tables64):
+    """Model-side resize (network/voxel_net_depth.py:197) of a depth map whose size is one of those where the
+    exact-rational nearest map differs from OpenCV's."""
+    rng = np.random.default_rng(12)
+    d = rng.random((198, 186), dtype=np.float32) * 4
+    assert not np.array_equal(orc.nearest_index(198, 1024), np.minimum(np.arange(1024) * 198 // 1024, 197))
+    assert np.array_equal(_voxelize(cam, d, 64)[0], orc.voxelize_depth(d, tables64.ray, 64, 2.0))
 
 
 def test_voxelize_batch_consistency_full_size(cam, tables64):

@@ -80,3 +80,27 @@ def test_stage_end_to_end(tabs):
     assert np.allclose(inter["logits"].reshape(2, 15, -1)[:, :, ::257].numpy(), g["logits_random_bn_s30"],
                        rtol=1e-4, atol=1e-4)
     assert float(inter["scene"][:, 32, 32, 0].min()) == 1.0
+
+
+def test_nearest_index_matches_cv2_golden():
+    """cv2.resize(INTER_NEAREST) index maps recorded from OpenCV itself (tests/make_golden.py): the oracle's rule
+    reproduces all of them, including the source sizes where floor(dst * n_src / n_dst) in exact arithmetic does not."""
+    g = util.golden("nearest_index.npz")
+    differs = 0
+    for key in g.files:
+        ns, nd = (int(t) for t in key.split("_"))
+        ref = g[key].astype(np.int64)
+        assert np.array_equal(orc.nearest_index(ns, nd), ref), key
+        differs += int(not np.array_equal(np.minimum(np.arange(nd) * ns // nd, ns - 1), ref))
+    assert differs >= 5          # the fixture does cover the cases that tell the two rules apart
+
+
+def test_dataset_preprocessing_restated(tabs):
+    """dataset/demo_dataset.py:86-91 on the raw demo EXRs (512x640): resize + clamp, then the occupancy golden."""
+    g = util.golden("voxel.npz")
+    raw = g["img_001796_raw"]
+    d = orc.preprocess_depth(raw)
+    assert d.shape == (1024, 1280) and d.dtype == np.float32 and d.max() <= 10.0
+    assert np.array_equal(orc.voxelize_depth(d, tabs[64].ray, 64, 2.0), util.unpack_bits(g["img_001796_v64"], 64))
+    already = np.full((1024, 1280), 12.5, np.float32)
+    assert np.array_equal(orc.preprocess_depth(already), np.full((1024, 1280), 10.0, np.float32))
