@@ -166,6 +166,11 @@ int sceneego_voxelize_depth_raw_f64(const float* d_depth_raw, int batch, int h, 
                                     double cuboid_side, float* d_occ_f32, void* d_occ_bf16,
                                     const sceneego_vol_layout_t* lay, int channel, void* stream);
 
+/* with_intersection (network/voxel_net_depth.py:257-260): volumes = cat([volumes, volumes * scene, scene]).
+ * In place on a plain planar bf16 volume whose channels [0,c) hold the lifted features and channel 2c the
+ * occupancy: writes channels [c,2c) = features * occupancy at every voxel. */
+int sceneego_intersect_bf16(void* d_vol, const sceneego_vol_layout_t* lay, int batch, int c, void* stream);
+
 /* Conversions between (B,C,S,S,S) f32 NCDHW and planar padded bf16 (for the
  * scene_volumes= input path, voxel_net_depth.py:246-249, and for tests). */
 int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
-    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64",
+    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16",
 ]
 
 
@@ -222,6 +222,12 @@ def voxelize_depth_raw(depth_raw: torch.Tensor, pre_hw, clamp_max: float, ray: t
         _ptr(depth_raw), b, h, w, int(pre_hw[0]), int(pre_hw[1]), C.c_float(clamp_max), _ptr(ray), int(img_h), int(img_w),
         int(volume_size), C.c_double(cuboid_side), _ptr(occ_f32), _ptr(occ_bf16),
         C.byref(lay) if lay is not None else None, int(channel), _stream()), "voxelize_depth_raw")
+
+
+def intersect(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int) -> None:
+    """channels [c,2c) = channels [0,c) * occupancy (channel 2c), in place (with_intersection)."""
+    _check(load_library().sceneego_intersect_bf16(_ptr(vol_bf16), C.byref(lay), int(batch), int(channels), _stream()),
+           "intersect")
 
 
 def pack_volume(x: torch.Tensor, out_bf16: torch.Tensor, lay: VolLayout, c_offset: int = 0) -> None:

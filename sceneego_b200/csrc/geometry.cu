@@ -411,6 +411,32 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------
+// with_intersection (network/voxel_net_depth.py:257-260): volumes = cat([volumes, volumes * scene, scene]).
+// In place on the planar bf16 V2V input: feature planes [0, C/8) -> planes [C/8, 2C/8) multiplied by the
+// occupancy value stored in channel 2C (exact: scene is 0 or 1).  One thread = one voxel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) intersect_kernel(__nv_bfloat16* __restrict__ vol, sceneego_vol_layout_t lay, int c8) {
+  const int S = lay.side;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= S * S * S) return;
+  const int z = n % S, y = (n / S) % S, x = n / (S * S);
+  const int64_t pos = vol_pos(lay, b, x, y, z);
+  const float sc = __bfloat162float(vol[((int64_t)(2 * c8) * lay.plane_stride + pos) * 8]);
+  for (int g = 0; g < c8; ++g) {
+    const uint4 in = *reinterpret_cast<const uint4*>(vol + ((int64_t)g * lay.plane_stride + pos) * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&in);
+    __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h[j]);
+      o[j] = __floats2bfloat162_rn(t.x * sc, t.y * sc);
+    }
+    *reinterpret_cast<uint4*>(vol + ((int64_t)(c8 + g) * lay.plane_stride + pos) * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // layout conversions (scene_volumes= input path; tests)
 // ---------------------------------------------------------------------------
 __global__ void pack_volume_kernel(const float* __restrict__ in, int c, int c_offset, __nv_bfloat16* __restrict__ out,
@@ -590,6 +616,15 @@ extern "C" int sceneego_voxelize_depth_raw_f64(const float* d_depth_raw, int bat
                                                const sceneego_vol_layout_t* lay, int channel, void* stream) {
   return voxelize_impl(d_depth_raw, batch, h, w, pre_h, pre_w, clamp_max, d_ray, img_h, img_w, V, side, d_occ_f32,
                        d_occ_bf16, lay, channel, stream);
+}
+
+extern "C" int sceneego_intersect_bf16(void* d_vol, const sceneego_vol_layout_t* lay, int batch, int c, void* stream) {
+  SE_REQUIRE(d_vol && lay && batch > 0 && batch <= 65535 && c > 0 && c % 8 == 0, "intersect: bad argument");
+  SE_REQUIRE(lay->s2d == 0, "intersect: plain planar layout only (the 65-channel stem does not use space-to-depth)");
+  const int N = lay->side * lay->side * lay->side;
+  intersect_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)d_vol, *lay, c / 8);
+  SE_CUDA_LAUNCH_CHECK("intersect");
+  return SCENEEGO_OK;
 }
 
 extern "C" int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, int c_offset, void* d_out,

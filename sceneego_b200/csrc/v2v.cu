@@ -626,6 +626,8 @@ static conv_tc_fn pick_conv_tc_pair(int ksteps, int tiles, int xs, int wrows) {
 }
 template <int WROWS>
 static conv_tc_fn pick_conv_tc_w(int ksteps, int tiles, int xs) {
+  if (WROWS == 0 && xs == 4 && ksteps == 5 && tiles == 2) return conv_tc_kernel<5, 2, 4, 0, 1>;   // 65-channel stem
+  if (WROWS == 0 && xs == 4 && ksteps == 5 && tiles == 1) return conv_tc_kernel<5, 1, 4, 0, 1>;   // (with_intersection)
   if (xs == 4 && ksteps == 3 && tiles == 4) return conv_tc_kernel<3, 4, 4, WROWS, 1>;
   if (xs == 4 && ksteps == 3 && tiles == 2) return conv_tc_kernel<3, 2, 4, WROWS, 1>;
   if (xs == 4 && ksteps == 2 && tiles == 4) return conv_tc_kernel<2, 4, 4, WROWS, 1>;

@@ -93,9 +93,11 @@ class VoxelNetwork_depth(nn.Module):
         self.with_intersection = False
         if self.with_scene is True:
             if config.model.with_intersection is True:
-                raise _lib.SceneEgoError("with_intersection=true (65-channel stem) is not built yet "
-                                         "(SURVEY.md section 8f item 4)")
-            volume_input_channel_num = 32 + 1
+                volume_input_channel_num = 32 + 1 + 32       # volumes, volumes * scene, scene (:66-68, :257-260)
+                self.with_intersection = True
+            else:
+                volume_input_channel_num = 32 + 1
+                self.with_intersection = False
         else:
             volume_input_channel_num = 32
         self.volume_net = V2VModel(volume_input_channel_num, self.num_joints, max_chunk=v2v_chunk).to(device)
@@ -185,7 +187,12 @@ class VoxelNetwork_depth(nn.Module):
                            extra_zero_planes=(pg.in_pad - 32) // 8)
             launches += 1
             if self.with_scene is True:
+                scene_ch = 64 if self.with_intersection else 32
                 if scene_volumes is not None:
+                    if self.with_intersection:
+                        # the reference concatenates 33 channels here and its 65-channel V2V then fails (:246-249)
+                        raise _lib.SceneEgoError("with_intersection=true takes depth_map_batch, not scene_volumes "
+                                                 "(the reference builds a 33-channel input on this path)")
                     sv = scene_volumes[s:s + n].contiguous().float().unsqueeze(1)
                     _lib.pack_volume(sv, in_buf, pg.lay_in, c_offset=32)
                 else:
@@ -195,10 +202,13 @@ class VoxelNetwork_depth(nn.Module):
                         ph, pw, cm = self.depth_preprocess
                         _lib.voxelize_depth_raw(d, (ph, pw), float(cm), self._ray_dev, self.image_height,
                                                 self.image_width, v, float(self.cuboid_side), None, in_buf, pg.lay_in,
-                                                channel=32)
+                                                channel=scene_ch)
                     else:
                         _lib.voxelize_depth(d, self._ray_dev, self.image_height, self.image_width, v,
-                                            float(self.cuboid_side), None, in_buf, pg.lay_in, channel=32)
+                                            float(self.cuboid_side), None, in_buf, pg.lay_in, channel=scene_ch)
+                    if self.with_intersection:
+                        _lib.intersect(in_buf, pg.lay_in, n, 32)
+                        launches += 1
                 launches += 1
             launches += vn.run_chunk(pg, n, logits[s:s + n])
         kp, volumes = _lib.softargmax3d(logits, float(self.volume_multiplier), bool(self.volume_softmax),

@@ -111,7 +111,51 @@ def make_nearest_index_golden():
     np.savez_compressed(os.path.join(OUT, "nearest_index.npz"), **out)
 
 
+def make_intersection_golden():
+    """with_intersection=true (network/voxel_net_depth.py:66-69,257-260): 65-channel V2V input
+    cat([volumes, volumes * scene, scene]).  The UNMODIFIED reference forward (B=1, V=64, CPU) on seeded synthetic
+    weights / features / depth; asserts oracle == reference and stores the reference's outputs."""
+    from oracle import sceneego_oracle as orc
+    from sceneego_b200.utils import synth
+    config, Net, cwd = import_reference()
+    config.opt.batch_size = 1
+    config.model.with_intersection = True
+    torch.manual_seed(0)
+    net = Net(config, device="cpu").eval()
+    shapes = [(k, tuple(v.shape)) for k, v in net.state_dict().items() if not k.startswith("backbone.")]
+    assert dict(shapes)["volume_net.front_layers.0.block.0.weight"] == (16, 65, 7, 7, 7)
+    tabs = orc.StageTables(os.path.join(REF, "utils/fisheye/fisheye.calibration_05_08.json"), 64, 2.0)
+    out = {}
+    report = json.load(open(os.path.join(OUT, "report.json")))
+    for mode in ("default", "random_bn"):
+        sd = synth.synthetic_state_dict(shapes, seed=0, mode=mode)
+        full = net.state_dict()
+        full.update(sd)
+        net.load_state_dict(full, strict=True)
+        feat = synth.synthetic_features(1, seed=7)
+        depth = synth.synthetic_depth_room(1, tabs.ray, seed=5)
+        net.backbone.forward = lambda images, _f=feat: (None, _f[: images.shape[0]])
+        with torch.no_grad():
+            kp_ref, _, vol_ref, _ = net(torch.zeros(1, 3, 256, 256), net.grid_coord_proj_batch, net.coord_volumes,
+                                        depth_map_batch=depth)
+            kp, _, vol, inter = orc.stage_forward(tabs, sd, feat, depth_batch=depth, with_intersection=True,
+                                                  return_intermediates=True)
+        e = orc.mpjpe(kp.numpy(), kp_ref.numpy())
+        assert e <= 5e-5, f"with_intersection stage keypoints differ {e}"
+        out[f"kp_{mode}"] = kp_ref.numpy()
+        out[f"logits_{mode}"] = inter["logits"].reshape(1, 15, -1)[:, :, ::257].numpy()
+        out[f"softmax_{mode}"] = vol_ref.reshape(1, 15, -1)[:, :, ::257].numpy()
+        report[f"stage_intersection_{mode}_mpjpe_oracle_vs_ref_m"] = e
+    out["state_dict_shapes"] = np.array(json.dumps([[k, list(sh)] for k, sh in shapes]))
+    np.savez_compressed(os.path.join(OUT, "stage_intersection_v64.npz"), **out)
+    json.dump(report, open(os.path.join(OUT, "report.json"), "w"), indent=1)
+    os.chdir(cwd)
+
+
 def main():
+    if "--intersection-only" in sys.argv:
+        make_intersection_golden()
+        return
     if "--nearest-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         make_nearest_index_golden()

@@ -135,3 +135,41 @@ def test_ragged_chunks_and_v128_configuration(tables64):
     torch.cuda.synchronize()
     assert torch.isfinite(a).all()
     assert ((a - b).norm() / b.norm()).item() <= 2e-2
+
+
+@pytest.mark.parametrize("mode", ["default", "random_bn"])
+def test_with_intersection_vs_reference(tables64, mode):
+    """with_intersection=true (network/voxel_net_depth.py:66-69,257-260): 65-channel V2V input
+    cat([volumes, volumes * scene, scene]) against the UNMODIFIED reference's outputs
+    (tests/golden/stage_intersection_v64.npz).  Same 0.5 mm MPJPE gate as the default configuration."""
+    import json
+    from sceneego_b200 import _lib
+    from sceneego_b200.network.voxel_net_depth import VoxelNetwork_depth
+    cfg = util.load_config(batch_size=1)
+    cfg.model.with_intersection = True
+    net = VoxelNetwork_depth(cfg, device="cuda").eval()
+    g = util.golden("stage_intersection_v64.npz")
+    ref_shapes = [(k, tuple(s)) for k, s in json.loads(str(g["state_dict_shapes"]))]
+    mine = [(k, tuple(v.shape)) for k, v in net.state_dict().items() if not k.startswith("backbone.")]
+    assert mine == ref_shapes and dict(mine)["volume_net.front_layers.0.block.0.weight"] == (16, 65, 7, 7, 7)
+    sd = synth.synthetic_state_dict(ref_shapes, seed=0, mode=mode)
+    full = net.state_dict()
+    full.update(sd)
+    net.load_state_dict(full, strict=True)
+    feat = synth.synthetic_features(1, seed=7)
+    depth = synth.synthetic_depth_room(1, tables64.ray, seed=5)
+    with torch.no_grad():
+        kp, _, volumes, _ = net.lift(feat.cuda(), net.grid_coord_proj_batch, net.coord_volumes, depth_map_batch=depth.cuda())
+    err_mm = orc.mpjpe(kp.cpu().numpy(), g[f"kp_{mode}"]) * 1000.0
+    print(f"MPJPE vs reference [with_intersection, {mode}]: {err_mm:.4f} mm")
+    assert err_mm <= 0.5
+    sm = volumes.reshape(1, 15, -1)[:, :, ::257].cpu().numpy()
+    assert np.allclose(sm, g[f"softmax_{mode}"], rtol=0.2, atol=1e-7)
+    # the V2V input the kernels built: channels 32..63 are channels 0..31 times the occupancy channel, bit for bit
+    pg = net.volume_net.program(64, 1, torch.device("cuda", 0))
+    x = _lib.unpack_volume(pg.buffers[pg.in_buf], pg.lay_in, 1, 65)
+    occ = torch.from_numpy(orc.voxelize_depth(depth[0].numpy(), tables64.ray, 64, 2.0)).cuda()
+    assert torch.equal(x[0, 64], occ)
+    assert torch.equal(x[0, 32:64], x[0, :32] * occ)
+    with pytest.raises(_lib.SceneEgoError):             # the reference's scene_volumes path feeds 33 channels to this net
+        net.lift(feat.cuda(), net.grid_coord_proj_batch, net.coord_volumes, scene_volumes=occ[None])
