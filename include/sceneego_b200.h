@@ -282,6 +282,21 @@ int sceneego_softargmax3d_f32(const float* d_logits, int batch, int joints, int 
                               float multiplier, int softmax, const float* d_axis, const float* d_coords,
                               float* d_keypoints, float* d_volumes_out, void* d_workspace, void* stream);
 
+/* ---- evaluation ------------------------------------ */
+
+/* The metric loop of test.py (dataset/test_dataset.py:102-112) for a batch of poses: replaces calculate_error
+ * (utils/calculate_errors.py:22-28), align_skeleton(estimated, gt, None, scale) (:60-91) and umeyama
+ * (utils/rigid_transform_with_scale.py:18-43).  fp64 like the reference's NumPy.
+ *   d_pred (B,J,3) f32 network output;  d_gt (B,J,3) f64
+ *   d_mpjpe[B], d_pampjpe[B]: per-frame mean joint distance before / after the per-frame similarity alignment
+ *                             (their means over B are the two numbers test.py prints); either may be NULL
+ *   d_aligned (B,J,3) f64 aligned poses, d_gt_out (B,J,3) f64 the ground truth align_skeleton returns
+ *                             (centred when scale == 0), d_transform (B,13) f64 = c, R row-major, t; any may be NULL
+ *   scale: 1 = pose.dot(R) * c + t;  0 = centre both poses first, pose.dot(R) + t */
+int sceneego_pose_errors_f64(const float* d_pred, const double* d_gt, int batch, int joints, int scale,
+                             double* d_mpjpe, double* d_pampjpe, double* d_aligned, double* d_gt_out,
+                             double* d_transform, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

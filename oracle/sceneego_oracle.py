@@ -345,6 +345,51 @@ def stage_forward(tables: StageTables, sd: Dict[str, torch.Tensor], feat256: tor
     return kp, features, vol
 
 
+# ----------------------------------------------------------------------------
+# evaluation math
+# ----------------------------------------------------------------------------
+def umeyama(P: np.ndarray, Q: np.ndarray):
+    """utils/rigid_transform_with_scale.py:18-43 -- (c, R, t) minimising sum |P c R + t - Q|^2."""
+    n = P.shape[0]
+    cP, cQ = P - P.mean(axis=0), Q - Q.mean(axis=0)
+    C = cP.T.dot(cQ) / n
+    V, S, W = np.linalg.svd(C)
+    if np.linalg.det(V) * np.linalg.det(W) < 0.0:
+        S[-1] = -S[-1]
+        V[:, -1] = -V[:, -1]
+    R = V.dot(W)
+    c = 1 / np.var(P, axis=0).sum() * np.sum(S)
+    t = Q.mean(axis=0) - P.mean(axis=0).dot(c * R)
+    return c, R, t
+
+
+def calculate_error(estimated_seq, gt_seq) -> float:
+    """utils/calculate_errors.py:22-28."""
+    d = np.linalg.norm(np.asarray(estimated_seq) - np.asarray(gt_seq), axis=2)
+    return float(np.mean(d))
+
+
+def align_skeleton(estimated_seq, gt_seq, scale: bool = True):
+    """utils/calculate_errors.py:60-91 with skeleton_model=None (what dataset/test_dataset.py:108 passes)."""
+    est = np.array(estimated_seq, copy=True)      # dtype kept: float32 network output stays float32, like deepcopy(np.asarray())
+    gt = np.array(gt_seq, copy=True)
+    out = np.zeros_like(est)
+    for s in range(est.shape[0]):
+        p, g = est[s], gt[s]
+        if scale is False:
+            p -= np.mean(p, axis=0)
+            g -= np.mean(g, axis=0)
+        c, R, t = umeyama(p, g)
+        out[s] = p.dot(R) * c + t if scale else p.dot(R) + t
+    return out, gt
+
+
+def evaluate_mpjpe(pred, gt):
+    """dataset/test_dataset.py:102-112."""
+    aligned, g = align_skeleton(pred, gt)
+    return calculate_error(pred, gt), calculate_error(aligned, g)
+
+
 def mpjpe(pred: np.ndarray, gt: np.ndarray) -> float:
     """utils/calculate_errors.py:22-28 semantics: mean per-joint L2 distance."""
     return float(np.mean(np.linalg.norm(np.asarray(pred) - np.asarray(gt), axis=-1)))

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
-    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16",
+    "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16", "sceneego_pose_errors_f64",
 ]
 
 
@@ -228,6 +228,22 @@ def intersect(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int)
     """channels [c,2c) = channels [0,c) * occupancy (channel 2c), in place (with_intersection)."""
     _check(load_library().sceneego_intersect_bf16(_ptr(vol_bf16), C.byref(lay), int(batch), int(channels), _stream()),
            "intersect")
+
+
+def pose_errors(pred: torch.Tensor, gt: torch.Tensor, scale: bool = True, want_aligned: bool = False):
+    """Per-frame MPJPE and PA-MPJPE (fp64) of pred (B,J,3) f32 against gt (B,J,3) f64; optionally the aligned poses,
+    the ground truth align_skeleton returns and the (c, R, t) transforms."""
+    b, j = pred.shape[0], pred.shape[1]
+    pred = pred.contiguous().float()
+    gt = gt.contiguous().double()
+    mp = torch.empty(b, dtype=torch.float64, device=pred.device)
+    pa = torch.empty(b, dtype=torch.float64, device=pred.device)
+    al = torch.empty(b, j, 3, dtype=torch.float64, device=pred.device) if want_aligned else None
+    go = torch.empty(b, j, 3, dtype=torch.float64, device=pred.device) if want_aligned else None
+    tr = torch.empty(b, 13, dtype=torch.float64, device=pred.device) if want_aligned else None
+    _check(load_library().sceneego_pose_errors_f64(_ptr(pred), _ptr(gt), b, j, int(bool(scale)), _ptr(mp), _ptr(pa),
+                                                   _ptr(al), _ptr(go), _ptr(tr), _stream()), "pose_errors")
+    return mp, pa, al, go, tr
 
 
 def pack_volume(x: torch.Tensor, out_bf16: torch.Tensor, lay: VolLayout, c_offset: int = 0) -> None:

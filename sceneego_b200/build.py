@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsceneego_b200.so")
-SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "tail.cu", "march.cu"]
+SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "tail.cu", "march.cu", "eval.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

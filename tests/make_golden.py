@@ -152,7 +152,48 @@ def make_intersection_golden():
     os.chdir(cwd)
 
 
+def make_eval_golden():
+    """Evaluation math: the reference's own umeyama (utils/rigid_transform_with_scale.py, imported unmodified) on
+    seeded pose pairs; calculate_error / align_skeleton (utils/calculate_errors.py imports the absent `utils_proj`
+    package, so those two are restated in the oracle and run here AROUND the reference's umeyama)."""
+    from oracle import sceneego_oracle as orc
+    sys.path.insert(0, REF)
+    import importlib
+    ref_rt = importlib.import_module("utils.rigid_transform_with_scale")
+    rng = np.random.default_rng(21)
+    B, J = 12, 15
+    gt = rng.normal(0, 0.4, (B, J, 3))                                   # float64 like the pickled ground truth
+    rot = np.linalg.qr(rng.normal(size=(B, 3, 3)))[0]
+    pred = (np.einsum("bjk,bkl->bjl", gt, rot) * rng.uniform(0.7, 1.3, (B, 1, 1)) + rng.normal(0, 0.3, (B, 1, 3))
+            + rng.normal(0, 0.02, (B, J, 3))).astype(np.float32)
+    pred[3] = (gt[3] * np.array([1.0, 1.0, -1.0])).astype(np.float32)    # a reflected pose: the det < 0 branch
+    gt[5, :, 2] = 0.25                                                   # planar ground truth
+    # exactly what the reference computes: float32 predictions (network output .cpu().numpy()), float64 ground truth,
+    # aligned poses stored back into a float32 array (np.zeros_like(estimated_seq), calculate_errors.py:73)
+    T = np.zeros((B, 13))
+    aligned = np.zeros_like(pred)
+    for b in range(B):
+        c, R, t = ref_rt.umeyama(pred[b], gt[b])
+        c2, R2, t2 = orc.umeyama(pred[b], gt[b])
+        assert abs(c - c2) <= 1e-12 and np.abs(R - R2).max() <= 1e-12 and np.abs(t - t2).max() <= 1e-12
+        T[b, 0], T[b, 1:10], T[b, 10:] = c, R.reshape(-1), t
+        aligned[b] = pred[b].dot(R) * c + t
+    al2, _ = orc.align_skeleton(pred, gt)
+    assert al2.dtype == np.float32 and np.array_equal(al2, aligned)
+    mp = float(np.mean(np.linalg.norm(pred - gt, axis=2)))
+    pa = float(np.mean(np.linalg.norm(aligned - gt, axis=2)))
+    assert orc.evaluate_mpjpe(pred, gt) == (mp, pa)
+    # the same in float64 throughout (what the device kernel computes from the float32 inputs)
+    al64, _ = orc.align_skeleton(pred.astype(np.float64), gt)
+    np.savez_compressed(os.path.join(OUT, "eval_poses.npz"), pred=pred, gt=gt, transform=T, aligned=aligned,
+                        mpjpe=np.array(mp), pampjpe=np.array(pa), aligned_f64=al64,
+                        pampjpe_f64=np.array(orc.calculate_error(al64, gt)))
+
+
 def main():
+    if "--eval-only" in sys.argv:
+        make_eval_golden()
+        return
     if "--intersection-only" in sys.argv:
         make_intersection_golden()
         return

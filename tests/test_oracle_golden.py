@@ -104,3 +104,21 @@ def test_dataset_preprocessing_restated(tabs):
     assert np.array_equal(orc.voxelize_depth(d, tabs[64].ray, 64, 2.0), util.unpack_bits(g["img_001796_v64"], 64))
     already = np.full((1024, 1280), 12.5, np.float32)
     assert np.array_equal(orc.preprocess_depth(already), np.full((1024, 1280), 10.0, np.float32))
+
+
+def test_evaluation_math_restated():
+    """umeyama / align_skeleton / calculate_error against the reference's own umeyama outputs
+    (tests/golden/eval_poses.npz, utils/rigid_transform_with_scale.py imported unmodified by make_golden)."""
+    g = util.golden("eval_poses.npz")
+    pred, gt = g["pred"], g["gt"]
+    for b in range(pred.shape[0]):
+        c, R, t = orc.umeyama(pred[b], gt[b])
+        assert abs(c - g["transform"][b, 0]) <= 1e-12
+        assert np.abs(R.reshape(-1) - g["transform"][b, 1:10]).max() <= 1e-12
+        assert np.abs(t - g["transform"][b, 10:]).max() <= 1e-12
+        assert abs(np.linalg.det(R) - 1.0) <= 1e-9                      # a rotation, also for the reflected pose
+    aligned, gt_out = orc.align_skeleton(pred, gt)
+    assert np.array_equal(aligned, g["aligned"]) and np.array_equal(gt_out, gt)
+    assert orc.evaluate_mpjpe(pred, gt) == (float(g["mpjpe"]), float(g["pampjpe"]))
+    a0, g0 = orc.align_skeleton(pred, gt, scale=False)                   # centred, rotation + translation only
+    assert np.abs(g0.mean(axis=1)).max() <= 1e-12 and np.abs(a0.mean(axis=1)).max() <= 1e-5
