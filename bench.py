@@ -197,8 +197,14 @@ def ours_arm(args):
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
+        # nvidia-smi's start-up (NVML initialisation over every GPU of the box) holds driver locks that stall kernel
+        # launches for tens of milliseconds: wait for its first sample so that only the 100 ms polling overlaps the
+        # timed region (a fresh box needed more than the 0.3 s this used to sleep and the step read 17 % slow)
         sampler.start()
-        time.sleep(0.3)
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 8.0:
+            time.sleep(0.05)
+        time.sleep(0.1)
     # ---- device-resident timing ----------------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

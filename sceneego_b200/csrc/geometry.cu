@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
                                                        W2CF32 cam, int h, int w, int V, float lo, float step,
                                                        int img_h, int img_w, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16,
-                                                       sceneego_vol_layout_t lay, int extra_zero_planes) {
+                                                       sceneego_vol_layout_t lay, int extra_zero_planes,
+                                                       int up_shift_y, int up_shift_x) {
   constexpr int C = 32;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
@@ -262,8 +263,11 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
     const int xs = X - pad;
     cell[t] = -1;
     if (inb && xs >= 0 && xs < img_h) {                                    // outside: ConstantPad2d zeros
-      const int sy = (int)(((long long)Y * h) / img_h);
-      const int sx = (int)(((long long)xs * w) / img_h);
+      // nearest source cell: Y * h / img_h.  The 64-bit divisions here (eight per voxel, ~100 instructions each)
+      // were what bounded the kernel; 1024 / 64 is a power of two, otherwise the 32-bit quotient is exact too
+      // (Y * h < 2^31, checked on the host)
+      const int sy = up_shift_y >= 0 ? (Y >> up_shift_y) : (int)((unsigned)(Y * h) / (unsigned)img_h);
+      const int sx = up_shift_x >= 0 ? (xs >> up_shift_x) : (int)((unsigned)(xs * w) / (unsigned)img_h);
       cell[t] = sy * w + sx;
     }
   }
@@ -369,14 +373,23 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
   const double q0 = rint(kPow2Side ? __dmul_rn(__dmul_rn(half, Vd), inv_side) : __ddiv_rn(__dmul_rn(half, Vd), side));
   const bool q0_in = q0 >= 0.0 && q0 <= hi;
   const int b_begin = blockIdx.z * frames_per_block;
-  for (int f = 0; f < frames_per_block; ++f) {
-    const int b = b_begin + f;
-    if (b >= batch) break;                                  // uniform over the block
-    float dv = 0.f;
-    if (in_src) {
-      dv = __ldcs(depth + ((size_t)b * h + sy) * w + sx);
-      dv = dv > nm.clamp_max ? nm.clamp_max : dv;             // NaN compares false and stays, like NumPy's mask
+  // all depth values of this pixel first (up to 8 independent loads in flight), then the arithmetic: one load per
+  // loop iteration behind a block-wide barrier left the kernel latency-bound at 0.9 TB/s
+  constexpr int kMaxFpb = 8;
+  float dvs[kMaxFpb];
+#pragma unroll
+  for (int f = 0; f < kMaxFpb; ++f) {
+    dvs[f] = 0.f;
+    if (f < frames_per_block && b_begin + f < batch && in_src) {
+      const float t = __ldcs(depth + ((size_t)(b_begin + f) * h + sy) * w + sx);
+      dvs[f] = t > nm.clamp_max ? nm.clamp_max : t;          // NaN compares false and stays, like NumPy's mask
     }
+  }
+#pragma unroll
+  for (int f = 0; f < kMaxFpb; ++f) {
+    const int b = b_begin + f;
+    if (f >= frames_per_block || b >= batch) break;         // uniform over the block
+    const float dv = dvs[f];
     int ix = -1, iy = 0, iz = 0;
     const bool zero = in_img && (dv == 0.0f);
     if (in_img && !zero) {
@@ -560,14 +573,22 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
   const float step = (float)((double)side / (V - 1));
   const float lo = (float)(-(double)side / 2);
   W2CF32 cam = calib ? make_w2c(calib) : W2CF32{};
+  SE_REQUIRE(h > 0 && w > 0 && (long long)img_w * (h > w ? h : w) < (1ll << 31), "unproject: image plane too large");
+  auto shift_of = [](int num, int den) {       // log2(num / den) when that ratio is an exact power of two, else -1
+    if (den <= 0 || num % den) return -1;
+    const int r = num / den;
+    for (int k = 0; k < 31; ++k) if ((1 << k) == r) return k;
+    return -1;
+  };
+  const int sh_y = shift_of(img_h, h), sh_x = shift_of(img_h, w);
   if (d_grid)
     unproject_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, d_grid, cam, h, w, V, lo, step, img_h,
                                                                     img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
-                                                                    extra_zero_planes);
+                                                                    extra_zero_planes, sh_y, sh_x);
   else
     unproject_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, nullptr, cam, h, w, V, lo, step, img_h,
                                                                    img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
-                                                                   extra_zero_planes);
+                                                                   extra_zero_planes, sh_y, sh_x);
   SE_CUDA_LAUNCH_CHECK("unproject");
   return SCENEEGO_OK;
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ void sa_merge(SaAcc& a, const SaAcc& b) {
 // grid: (splits, B*J).  Each CTA reduces `chunk` consecutive voxels of one joint volume.
 template <bool kSoftmax, bool kAxis>
 __global__ void __launch_bounds__(SA_THREADS) softargmax_partial_kernel(
-    const float* __restrict__ logits, int N, int V, int chunk, float mult, const float* __restrict__ axis,
+    const float* __restrict__ logits, int N, int V, int log2v, int chunk, float mult, const float* __restrict__ axis,
     const float* __restrict__ coords, float* __restrict__ partial) {
   extern __shared__ float s_axis[];  // 3*V when kAxis
   if (kAxis) {
@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(SA_THREADS) softargmax_partial_kernel(
         w[q] = kSoftmax ? exp2f((e[q] * mult - a.m) * kLog2e) : fmaxf(e[q] * mult, 0.f);
       const int n0 = idx[u] * 4;
       if (kAxis) {  // V % 4 == 0: the four voxels share x and y
-        const int z0 = n0 % V, y = (n0 / V) % V, x = n0 / (V * V);
+        // power-of-two sides (64, 128): shifts instead of three runtime integer divisions per float4
+        const int z0 = log2v >= 0 ? (n0 & (V - 1)) : n0 % V;
+        const int y = log2v >= 0 ? ((n0 >> log2v) & (V - 1)) : (n0 / V) % V;
+        const int x = log2v >= 0 ? (n0 >> (2 * log2v)) : n0 / (V * V);
         const float ws = (w[0] + w[1]) + (w[2] + w[3]);
         a.s += ws;
         a.sx = fmaf(ws, s_axis[x], a.sx);
@@ -196,13 +199,15 @@ extern "C" int sceneego_softargmax3d_f32(const float* d_logits, int batch, int j
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(splits, BJ);
   const size_t smem = d_axis ? 3 * V * sizeof(float) : 0;
+  int log2v = -1;
+  for (int k = 0; k < 12; ++k) if ((1 << k) == V) log2v = k;
   if (softmax) {
-    if (d_axis) softargmax_partial_kernel<true, true><<<grid, SA_THREADS, smem, st>>>(d_logits, N, V, chunk, mult, d_axis, nullptr, partial);
-    else softargmax_partial_kernel<true, false><<<grid, SA_THREADS, 0, st>>>(d_logits, N, V, chunk, mult, nullptr, d_coords, partial);
+    if (d_axis) softargmax_partial_kernel<true, true><<<grid, SA_THREADS, smem, st>>>(d_logits, N, V, log2v, chunk, mult, d_axis, nullptr, partial);
+    else softargmax_partial_kernel<true, false><<<grid, SA_THREADS, 0, st>>>(d_logits, N, V, log2v, chunk, mult, nullptr, d_coords, partial);
     softargmax_combine_kernel<true><<<(BJ + 127) / 128, 128, 0, st>>>(partial, splits, BJ, d_kp, stats);
   } else {
-    if (d_axis) softargmax_partial_kernel<false, true><<<grid, SA_THREADS, smem, st>>>(d_logits, N, V, chunk, mult, d_axis, nullptr, partial);
-    else softargmax_partial_kernel<false, false><<<grid, SA_THREADS, 0, st>>>(d_logits, N, V, chunk, mult, nullptr, d_coords, partial);
+    if (d_axis) softargmax_partial_kernel<false, true><<<grid, SA_THREADS, smem, st>>>(d_logits, N, V, log2v, chunk, mult, d_axis, nullptr, partial);
+    else softargmax_partial_kernel<false, false><<<grid, SA_THREADS, 0, st>>>(d_logits, N, V, log2v, chunk, mult, nullptr, d_coords, partial);
     softargmax_combine_kernel<false><<<(BJ + 127) / 128, 128, 0, st>>>(partial, splits, BJ, d_kp, stats);
   }
   SE_CUDA_LAUNCH_CHECK("softargmax");
