@@ -226,7 +226,7 @@ def ours_arm(args):
 
     # ---- end to end: pinned host buffers -> H2D -> lift -> D2H, through the public pipeline ----
     pipe = HostStagePipeline(net, gather_fn=gather if world > 1 else None)
-    pipe.run([(feat_h, depth_h)] * 2)
+    pipe.run([(feat_h, depth_h)] * args.steps)        # same batch count as the timed call: pinned result buffers exist
     barrier()
     pipe.h2d_bytes = pipe.d2h_bytes = 0
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -185,9 +185,12 @@ def feature_conv1x1(feat: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     return out
 
 
-def features_upsample_pad(feat_cl: torch.Tensor, up: int, pad: int) -> torch.Tensor:
+def features_upsample_pad(feat_cl: torch.Tensor, up: int, pad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     b, h, w, c = feat_cl.shape
-    out = torch.empty(b, c, up, up + 2 * pad, dtype=torch.float32, device=feat_cl.device)
+    if out is None:
+        out = torch.empty(b, c, up, up + 2 * pad, dtype=torch.float32, device=feat_cl.device)
+    elif tuple(out.shape) != (b, c, up, up + 2 * pad) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise SceneEgoError("features_upsample_pad: bad output buffer")
     _check(load_library().sceneego_features_upsample_pad_f32(_ptr(feat_cl), _ptr(out), b, c, h, w, up, pad,
                                                               _stream()), "features_upsample_pad")
     return out

@@ -120,6 +120,7 @@ class VoxelNetwork_depth(nn.Module):
         self._axis = torch.stack([cv[:, 0, 0, 0], cv[0, :, 0, 1], cv[0, 0, :, 2]]).contiguous()
         self.last_launches = 0
         self._side_stream = None
+        self._features_buf = None
         # (pre_h, pre_w, clamp_max): depth_map_batch holds RAW decoded maps and the dataset's preprocessing
         # (dataset/demo_dataset.py:86-91: nearest resize to 1280x1024, depth > 10 -> 10) is fused into the
         # voxelisation kernel's load; None: the caller has preprocessed them, like the reference's datasets do
@@ -156,13 +157,22 @@ class VoxelNetwork_depth(nn.Module):
                 self._side_stream = torch.cuda.Stream(device=feat.device)
             side = self._side_stream
             side.wait_stream(main)
+            # one persistent buffer per batch size (168 MB per frame): a fresh 10 GB tensor per call, kept alive across
+            # two streams by record_stream, made the caching allocator run out of reusable blocks as soon as the host
+            # ran a few steps ahead of the GPU and fall back to synchronising cudaFree / cudaMalloc cycles.  The
+            # returned tensor is therefore overwritten by the next call (clone it to keep it); consumers on the
+            # current stream are ordered after the writer, and the next call's writer after them.
+            shape = (b, 32, self.image_height, self.image_width)
+            if self._features_buf is None or tuple(self._features_buf.shape) != shape:
+                self._features_buf = None
+                self._features_buf = torch.empty(shape, dtype=torch.float32, device=feat.device)
             with torch.cuda.stream(side):
                 features = _lib.features_upsample_pad(feat32, self.image_height,
-                                                      (self.image_width - self.image_height) // 2)
+                                                      (self.image_width - self.image_height) // 2,
+                                                      out=self._features_buf)
                 feat_done = torch.cuda.Event()
                 feat_done.record(side)
             feat32.record_stream(side)
-            features.record_stream(main)
             launches += 1
         if self.with_scene is True and scene_volumes is None and depth_map_batch is None:
             print("no scene volume or depth input!")
