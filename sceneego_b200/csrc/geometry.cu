@@ -221,13 +221,16 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
                                                        int img_h, int img_w, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16,
                                                        sceneego_vol_layout_t lay, int extra_zero_planes,
-                                                       int up_shift_y, int up_shift_x) {
+                                                       int up_shift_y, int up_shift_x, int log2v) {
   constexpr int C = 32;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   const int N = V * V * V;
   if (n >= N) return;
-  const int vz = n % V, vy = (n / V) % V, vx = n / (V * V);
+  // power-of-two sides: shifts instead of runtime integer divisions
+  const int vz = log2v >= 0 ? (n & (V - 1)) : n % V;
+  const int vy = log2v >= 0 ? ((n >> log2v) & (V - 1)) : (n / V) % V;
+  const int vx = log2v >= 0 ? (n >> (2 * log2v)) : n / (V * V);
   float gx, gy;
   if (kProject) {
     float px, py;
@@ -580,15 +583,15 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
     for (int k = 0; k < 31; ++k) if ((1 << k) == r) return k;
     return -1;
   };
-  const int sh_y = shift_of(img_h, h), sh_x = shift_of(img_h, w);
+  const int sh_y = shift_of(img_h, h), sh_x = shift_of(img_h, w), log2v = shift_of(V, 1);
   if (d_grid)
     unproject_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, d_grid, cam, h, w, V, lo, step, img_h,
                                                                     img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
-                                                                    extra_zero_planes, sh_y, sh_x);
+                                                                    extra_zero_planes, sh_y, sh_x, log2v);
   else
     unproject_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, nullptr, cam, h, w, V, lo, step, img_h,
                                                                    img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
-                                                                   extra_zero_planes, sh_y, sh_x);
+                                                                   extra_zero_planes, sh_y, sh_x, log2v);
   SE_CUDA_LAUNCH_CHECK("unproject");
   return SCENEEGO_OK;
 }
