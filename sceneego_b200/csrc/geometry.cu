@@ -135,49 +135,79 @@ __global__ void __launch_bounds__(256) grid_sample_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------
-// a1: 1x1 Conv2d 256 -> 32 (+bias), NCHW f32 in, channel-last f32 out.
-// One CTA = 64 pixels x 32 output channels; K streamed through smem in chunks of 32.
+// a1: 1x1 Conv2d 256 -> 32 (+bias), NCHW f32 in, channel-last f32 out.  HBM-bound (4.2 MB read per frame).
+// One CTA = 128 pixels x 32 output channels; each thread owns a 4 pixel x 4 channel register tile, so one
+// LDS.128 of inputs and one of weights feed 16 FMAs (the first version: 9 shared loads per 8 FMAs, 1.3 TB/s).
+// K is streamed through shared memory in chunks of 32 channels; the next chunk's global loads are in flight
+// while the current one is multiplied.  Same accumulation order as a sequential dot product (k ascending, fmaf).
 // ---------------------------------------------------------------------------
-constexpr int FC_PIX = 64, FC_KC = 32, FC_CO = 32;
+constexpr int FC_PIX = 128, FC_KC = 32, FC_CO = 32;
 
 __global__ void __launch_bounds__(256) feature_conv1x1_kernel(const float* __restrict__ feat,
                                                              const float* __restrict__ weight,
                                                              const float* __restrict__ bias,
                                                              float* __restrict__ out, int cin, int hw) {
-  __shared__ float s_in[FC_KC][FC_PIX];      // [k][pixel]
-  __shared__ float s_w[FC_KC][FC_CO + 1];    // [k][co]
+  __shared__ __align__(16) float s_in[FC_KC][FC_PIX];     // [k][pixel]
+  __shared__ __align__(16) float s_w[FC_KC][FC_CO];       // [k][co]
   const int b = blockIdx.y;
   const int pix0 = blockIdx.x * FC_PIX;
   const int tid = threadIdx.x;
-  const int co = tid & 31;        // lane -> output channel (channel-last store is coalesced)
-  const int pg = tid >> 5;        // 8 pixel groups of 8 pixels
-  float acc[8];
+  const int cg = tid & 7;          // channels 4*cg .. 4*cg+3
+  const int pg = tid >> 3;         // pixels   4*pg .. 4*pg+3
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const float* fb = feat + (size_t)b * cin * hw;
-  for (int k0 = 0; k0 < cin; k0 += FC_KC) {
-    for (int i = tid; i < FC_KC * FC_PIX; i += 256) {
-      const int kk = i / FC_PIX, p = i % FC_PIX;
-      s_in[kk][p] = (pix0 + p < hw) ? fb[(size_t)(k0 + kk) * hw + pix0 + p] : 0.f;
+  const bool vec = (hw % 4 == 0) && (pix0 + FC_PIX <= hw);
+  float4 rin[4];
+  float rw[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;                   // float4 index inside the [32][128] chunk
+      const int kk = e >> 5, p4 = (e & 31) * 4;
+      const float* src = fb + (size_t)(k0 + kk) * hw + pix0 + p4;
+      if (vec) rin[i] = __ldcs(reinterpret_cast<const float4*>(src));
+      else {
+        rin[i].x = pix0 + p4 + 0 < hw ? src[0] : 0.f; rin[i].y = pix0 + p4 + 1 < hw ? src[1] : 0.f;
+        rin[i].z = pix0 + p4 + 2 < hw ? src[2] : 0.f; rin[i].w = pix0 + p4 + 3 < hw ? src[3] : 0.f;
+      }
+      // weight element kk = e / 32, co = e % 32: lanes walk co, so the shared-memory store below is conflict-free
+      // (the 32 KB weight matrix is L2-resident; its strided 4-byte reads do not matter)
+      rw[i] = weight[(size_t)(e & 31) * cin + k0 + (e >> 5)];
     }
-    for (int i = tid; i < FC_KC * FC_CO; i += 256) {
-      const int c = i / FC_KC, kk = i % FC_KC;
-      s_w[kk][c] = weight[(size_t)c * cin + k0 + kk];
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < cin; k0 += FC_KC) {
+    __syncthreads();                                 // the previous chunk has been consumed
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      *reinterpret_cast<float4*>(&s_in[e >> 5][(e & 31) * 4]) = rin[i];
+      s_w[e >> 5][e & 31] = rw[i];
     }
     __syncthreads();
+    if (k0 + FC_KC < cin) fetch(k0 + FC_KC);
 #pragma unroll 8
     for (int kk = 0; kk < FC_KC; ++kk) {
-      const float w = s_w[kk][co];
+      const float4 x = *reinterpret_cast<const float4*>(&s_in[kk][4 * pg]);
+      const float4 w = *reinterpret_cast<const float4*>(&s_w[kk][4 * cg]);
+      const float xs[4] = {x.x, x.y, x.z, x.w}, ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(s_in[kk][pg * 8 + i], w, acc[i]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ws[j], acc[i][j]);
     }
-    __syncthreads();
   }
-  const float bv = bias[co];
+  const float4 bv = make_float4(bias[4 * cg], bias[4 * cg + 1], bias[4 * cg + 2], bias[4 * cg + 3]);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int p = pix0 + pg * 8 + i;
-    if (p < hw) out[((size_t)b * hw + p) * FC_CO + co] = acc[i] + bv;
+  for (int i = 0; i < 4; ++i) {
+    const int p = pix0 + 4 * pg + i;
+    if (p < hw)
+      *reinterpret_cast<float4*>(out + ((size_t)b * hw + p) * FC_CO + 4 * cg) =
+          make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
   }
 }
 
@@ -346,12 +376,14 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
                                                       double side, double inv_side, float* __restrict__ occ_f32,
                                                       __nv_bfloat16* __restrict__ occ_bf16,
                                                       sceneego_vol_layout_t lay, int channel, int batch, int frames_per_block) {
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  // threads cover the img_h source columns only; the zero-padded columns (np.pad, :198) all land on the
+  // zero-depth voxel, which one thread of the launch sets when there is any padding
+  const int xs = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y;
   const int pad = (img_w - img_h) / 2;
-  const int xs = X - pad;
-  const bool in_img = X < img_w;
-  const bool in_src = in_img && xs >= 0 && xs < img_h;
+  const int X = xs + pad;
+  const bool in_src = xs < img_h;
+  const bool in_img = in_src;
   // cv2.resize(INTER_NEAREST), model side then dataset side
   int sy = (int)floor(__dmul_rn((double)Y, nm.ify1));
   int sx = (int)floor(__dmul_rn((double)(in_src ? xs : 0), nm.ifx1));
@@ -410,8 +442,10 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
         ix = (int)qx; iy = (int)qy; iz = (int)qz;
       }
     }
-    // one thread per block writes the zero-depth voxel when any pixel of the block has zero depth
-    const int any_zero = __syncthreads_or(zero ? 1 : 0);
+    // one thread per block writes the zero-depth voxel when any pixel of the block has zero depth (a per-warp vote
+    // instead of the block-wide one made 8x more writers hammer the same voxel: 3.6 -> 4.6 us); block (0,0,z) also
+    // does it for the padded columns
+    const bool any_zero = __syncthreads_or(zero ? 1 : 0) != 0 || (pad > 0 && blockIdx.x == 0 && blockIdx.y == 0);
     if (any_zero && threadIdx.x == 0 && q0_in) {
       const int c = (int)q0;
       if (occ_f32) occ_f32[(((size_t)b * V + c) * V + c) * V] = 1.0f;
@@ -605,7 +639,7 @@ static int voxelize_impl(const float* d_depth, int batch, int h, int w, int pre_
   SE_REQUIRE(!d_occ_bf16 || !lay->s2d || channel % 8 == 0, "voxelize: s2d occupancy follows whole channel groups");
   // several frames per block so that a pixel's ray is fetched once for all of them (grid.z <= 65535 either way)
   const int fpb = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
-  dim3 grid((img_w + 255) / 256, img_h, (batch + fpb - 1) / fpb);
+  dim3 grid((img_h + 255) / 256, img_h, (batch + fpb - 1) / fpb);     // source columns only
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
   NearestMaps nm;
   // OpenCV: inv_scale = (double)dsize / ssize; ifx = 1. / inv_scale
