@@ -280,6 +280,23 @@ def v2v_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = "") 
     return F.conv3d(x, sd["output_layer.weight"], sd["output_layer.bias"])
 
 
+def v2v_simple_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """network/v2v.py:184-241 -- V2VModelSimple / EncoderDecoderSimple (two pooling levels, one 1x1 back layer)."""
+    e = "encoder_decoder."
+    x = _basic(sd, "front_layers.0", x)
+    skip1 = _res(sd, e + "skip_res1", x)
+    x = _res(sd, e + "encoder_res1", F.max_pool3d(x, 2, 2))
+    skip2 = _res(sd, e + "skip_res2", x)
+    x = _res(sd, e + "encoder_res2", F.max_pool3d(x, 2, 2))
+    x = _res(sd, e + "mid_res", x)
+    x = _res(sd, e + "decoder_res2", x)
+    x = _up(sd, e + "decoder_upsample2", x) + skip2
+    x = _res(sd, e + "decoder_res1", x)
+    x = _up(sd, e + "decoder_upsample1", x) + skip1
+    x = _basic(sd, "back_layers.0", x)
+    return F.conv3d(x, sd["output_layer.weight"], sd["output_layer.bias"])
+
+
 # ----------------------------------------------------------------------------
 # a8: soft-argmax
 # ----------------------------------------------------------------------------

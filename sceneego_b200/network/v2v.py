@@ -90,7 +90,7 @@ def _pad16(c: int) -> int:
 class _Program:
     """Op list + buffer pool + packed weight blob for one (volume_size, chunk) pair."""
 
-    def __init__(self, side: int, chunk: int, in_channels: int, device):
+    def __init__(self, side: int, chunk: int, in_channels: int, device, allow_s2d: bool = True):
         self.side, self.chunk, self.device = side, chunk, device
         self.ops: List[_lib.V2VOp] = []
         self.buffers: List[torch.Tensor] = []
@@ -102,7 +102,7 @@ class _Program:
         self.in_pad = _pad16(in_channels)
         # stem input.  33 channels (32 lifted features + occupancy): space-to-depth storage read by the
         # 2x2x2-stacked stem kernel (csrc/stem.cu); anything else: plain layout, 7^3 stencil needs 3 zero cells
-        self.s2d = in_channels == 33
+        self.s2d = in_channels == 33 and allow_s2d
         self.lay_in = _lib.vol_layout_s2d(side, chunk) if self.s2d else _lib.vol_layout(side, 3, chunk)
         self.lays = [_lib.vol_layout(side >> l, 1, chunk) for l in range(6)]
         self.level_channels = EncoderDecorder.CHANNELS
@@ -502,6 +502,100 @@ class V2VModel(nn.Module):
                     total += 2 * m.in_channels * m.out_channels * 8 * (s // 2) ** 3
                 else:
                     total += 2 * m.in_channels * m.out_channels * k ** 3 * s ** 3
+        return total
+
+
+class EncoderDecoderSimple(nn.Module):
+    """v2v.py:184-221: two pool/res levels (32 -> 64 -> 128), mid res, two res/upsample levels with skips."""
+
+    def __init__(self):
+        super().__init__()
+        self.encoder_pool1 = Pool3DBlock(2)
+        self.encoder_res1 = Res3DBlock(32, 64)
+        self.encoder_pool2 = Pool3DBlock(2)
+        self.encoder_res2 = Res3DBlock(64, 128)
+        self.mid_res = Res3DBlock(128, 128)
+        self.decoder_res2 = Res3DBlock(128, 128)
+        self.decoder_upsample2 = Upsample3DBlock(128, 64, 2, 2)
+        self.decoder_res1 = Res3DBlock(64, 64)
+        self.decoder_upsample1 = Upsample3DBlock(64, 32, 2, 2)
+        self.skip_res1 = Res3DBlock(32, 32)
+        self.skip_res2 = Res3DBlock(64, 64)
+
+
+class V2VModelSimple(V2VModel):
+    """network/v2v.py:224-257 -- the shallow V2V variant (not reachable from VoxelNetwork_depth, which builds
+    V2VModel; provided for users of the reference class).  Same state-dict names as the reference; the same op
+    program machinery: 7^3 stem with 32 outputs on conv_tc_kernel (plain padded input), the 32-channel Res block on
+    the marching kernel, 64/128-channel blocks, pools and transposed convs as in V2VModel, the two trailing 1x1
+    convs unfused."""
+
+    def __init__(self, input_channels, output_channels, max_chunk: int = 32):
+        nn.Module.__init__(self)
+        self.input_channels, self.output_channels = input_channels, output_channels
+        self.max_chunk = max_chunk
+        self.c32_xstack, self.fuse_shortcut, self.cta_pair, self.march = 2, True, 2, True
+        self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 32, 7))
+        self.encoder_decoder = EncoderDecoderSimple()
+        self.back_layers = nn.Sequential(Basic3DBlock(32, 32, 1))
+        self.output_layer = nn.Conv3d(32, output_channels, kernel_size=1, stride=1, padding=0)
+        self._initialize_weights()
+        self._programs = {}
+        self._weights_version = None
+
+    def _build(self, side: int, chunk: int, device) -> _Program:
+        if side % 4 != 0:
+            raise _lib.SceneEgoError("V2VModelSimple needs a volume side divisible by 4 (two 2x poolings)")
+        pg = _Program(side, chunk, self.input_channels, device, allow_s2d=False)
+        ed = self.encoder_decoder
+        x = pg.acquire(0)
+        pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True)
+        skip1 = self._res(pg, ed.skip_res1, x, 0)
+        p = pg.acquire(1)
+        pg.pool(x, p, 32)
+        pg.release(x)
+        x = self._res(pg, ed.encoder_res1, p, 1)
+        pg.release(p)
+        skip2 = self._res(pg, ed.skip_res2, x, 1)
+        p = pg.acquire(2)
+        pg.pool(x, p, 64)
+        pg.release(x)
+        x = self._res(pg, ed.encoder_res2, p, 2)
+        pg.release(p)
+        for blk in (ed.mid_res, ed.decoder_res2):
+            y = self._res(pg, blk, x, 2)
+            pg.release(x)
+            x = y
+        u = pg.acquire(1)
+        pg.deconv(ed.decoder_upsample2.block[0], ed.decoder_upsample2.block[1], x, u, add=skip2)
+        pg.release(x)
+        pg.release(skip2)
+        x = self._res(pg, ed.decoder_res1, u, 1)
+        pg.release(u)
+        u = pg.acquire(0)
+        pg.deconv(ed.decoder_upsample1.block[0], ed.decoder_upsample1.block[1], x, u, add=skip1)
+        pg.release(x)
+        pg.release(skip1)
+        y = pg.acquire(0)
+        pg.conv(self.back_layers[0].block[0], self.back_layers[0].block[1], u, y, relu=True)
+        pg.release(u)
+        pg.buffers.append(torch.empty(0, device=device))
+        pg.buf_level.append(0)
+        pg.logits_buf = len(pg.buffers) - 1
+        pg.conv(self.output_layer, None, y, pg.logits_buf, relu=False, out_f32=True)
+        pg.finalize()
+        return pg
+
+    def flops_per_frame(self, side: int) -> int:
+        total = 0
+        for name, m in self.named_modules():
+            if isinstance(m, nn.ConvTranspose3d):
+                lvl = int(name.split(".")[1][-1])
+                total += 2 * m.in_channels * m.out_channels * 8 * (side >> lvl) ** 3
+            elif isinstance(m, nn.Conv3d):
+                part = name.split(".")[1] if name.startswith("encoder_decoder.") else ""
+                lvl = 0 if not part else 2 if part == "mid_res" else (int(part[-1]) - 1 if part.startswith("skip_res") else int(part[-1]))
+                total += 2 * m.in_channels * m.out_channels * m.kernel_size[0] ** 3 * (side >> lvl) ** 3
         return total
 
 

@@ -190,7 +190,38 @@ def make_eval_golden():
                         pampjpe_f64=np.array(orc.calculate_error(al64, gt)))
 
 
+def make_v2v_simple_golden():
+    """V2VModelSimple (network/v2v.py:224-257) at V=32, B=1: the reference class itself on seeded weights."""
+    from oracle import sceneego_oracle as orc
+    from sceneego_b200.utils import synth
+    sys.path.insert(0, REF)
+    from network.v2v import V2VModelSimple
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 33, 32, 32, 32, generator=g).abs()
+    x[:, 32] = (x[:, 32] > 1.0).float()
+    out = {}
+    report = json.load(open(os.path.join(OUT, "report.json")))
+    m = V2VModelSimple(33, 15).eval()
+    shapes = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    for mode in ("default", "random_bn"):
+        vs = synth.synthetic_state_dict(shapes, seed=2, mode=mode)
+        m.load_state_dict(vs, strict=True)
+        with torch.no_grad():
+            ref = m(x)
+            got = orc.v2v_simple_forward(vs, x)
+        e = (ref - got).abs().max().item()
+        assert e <= 1e-5 * max(1.0, ref.abs().max().item()), f"v2v simple differs {e}"
+        out[mode] = ref.reshape(15, -1)[:, ::13].numpy()
+        report[f"v2v_simple32_{mode}_max_abs_vs_ref"] = e
+    out["state_dict_shapes"] = np.array(json.dumps([[k, list(sh)] for k, sh in shapes]))
+    np.savez_compressed(os.path.join(OUT, "v2v_simple_v32.npz"), **out)
+    json.dump(report, open(os.path.join(OUT, "report.json"), "w"), indent=1)
+
+
 def main():
+    if "--simple-only" in sys.argv:
+        make_v2v_simple_golden()
+        return
     if "--eval-only" in sys.argv:
         make_eval_golden()
         return

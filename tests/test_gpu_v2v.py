@@ -340,3 +340,26 @@ def test_fused_tail_matches_unfused_chain():
     scale = plain.abs().max().item()
     assert (fused - plain).abs().max().item() <= 8e-3 * scale      # one bf16 ulp of the hidden activations, propagated
     assert ((fused - plain).norm() / plain.norm()).item() <= 2e-3
+
+
+@pytest.mark.parametrize("mode", ["default", "random_bn"])
+def test_v2v_simple_vs_reference_golden(mode):
+    """V2VModelSimple at V=32 against outputs of the UNMODIFIED reference class (tests/golden/v2v_simple_v32.npz).
+    Tolerance as for V2VModel: bf16 activations -> 3 % of the logit range, 1.5 % Frobenius."""
+    import json
+    from sceneego_b200.network.v2v import V2VModelSimple
+    from sceneego_b200.utils import synth
+    g = util.golden("v2v_simple_v32.npz")
+    shapes = [(k, tuple(s)) for k, s in json.loads(str(g["state_dict_shapes"]))]
+    m = V2VModelSimple(33, 15).eval()
+    m.load_state_dict(synth.synthetic_state_dict(shapes, seed=2, mode=mode), strict=True)
+    m = m.cuda()
+    x = torch.randn(1, 33, 32, 32, 32, generator=torch.Generator().manual_seed(6)).abs()
+    x[:, 32] = (x[:, 32] > 1.0).float()
+    with torch.no_grad():
+        out = m(x.cuda())
+    ref = torch.from_numpy(g[mode])
+    got = out.reshape(15, -1)[:, ::13].cpu()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 3e-2 * scale
+    assert ((got - ref).norm() / ref.norm()).item() <= 1.5e-2

@@ -239,3 +239,28 @@ def test_march_packing_walked_like_the_kernel_reproduces_conv3d():
         ref = F.conv3d(x.double(), wq.to(torch.bfloat16).double(), padding=1)[0].numpy()
         ref += ((conv.bias - bn.running_mean) * bn.weight / torch.sqrt(bn.running_var + bn.eps) + bn.bias).double().numpy()[:, None, None, None]
     assert np.abs(out - ref).max() <= 1e-5
+
+
+def test_v2v_simple_structure_matches_reference():
+    """V2VModelSimple (network/v2v.py:224-257): the reference's state-dict names/shapes (recorded by make_golden from
+    the reference class) and an op program that reads only what earlier ops wrote."""
+    import json
+    from sceneego_b200.network.v2v import V2VModelSimple
+    m = V2VModelSimple(33, 15)
+    ref_shapes = [(k, tuple(s)) for k, s in json.loads(str(util.golden("v2v_simple_v32.npz")["state_dict_shapes"]))]
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == ref_shapes
+    pg = m.program(32, 1, torch.device("cpu"))
+    kinds = [op.type for op in pg.ops]
+    assert kinds.count(_lib.OP_MAXPOOL2) == 2 and kinds.count(_lib.OP_DECONV2) == 2
+    assert kinds.count(_lib.OP_CONV3_MARCH) == 2                      # skip_res1: the only 32-channel Res block
+    # stem + 6 Res blocks on conv_tc (two 3^3 convs each; the two projection shortcuts are fused) + back 1x1 + output
+    assert kinds.count(_lib.OP_CONV) == 1 + 6 * 2 + 2
+    assert pg.ops[0].ksize == 7 and pg.ops[0].cout == 32 and pg.ops[0].lay_src.s2d == 0 and pg.ops[0].lay_src.pad == 3
+    assert pg.ops[-1].flags & _lib.F_OUT_F32 and pg.ops[-1].cout_real == 15
+    assert pg.flops == m.flops_per_frame(32)
+    written = {pg.in_buf}
+    for op in pg.ops:
+        assert op.src in written and op.src != op.dst
+        if op.res >= 0:
+            assert op.res in written
+        written.add(op.dst)
