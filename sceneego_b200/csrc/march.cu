@@ -393,6 +393,14 @@ int launch_conv_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const
   SE_REQUIRE((uint64_t)p.w_bytes + p.w2_bytes + 2ull * p.stage_bytes + fixed <= smem_cap,
              "v2v_run: op %d: resident weights + two window stages exceed shared memory", op_index);
   int stages = (int)((smem_cap - p.w_bytes - p.w2_bytes - fixed) / p.stage_bytes);
+  if (two) {
+    // two CTAs at ~107 KB each leave the SM ~12 KB of L1 for the epilogue's residual loads and stores: three window
+    // stages measured 3 % SLOWER than two on the 32 -> 32 layers (12.5 vs 12.1 us).  Keep each CTA under 92 KB
+    // (>= 44 KB of L1) unless that would leave fewer than two stages.
+    int capped = (int)(((int64_t)92 * 1024 - p.w_bytes - p.w2_bytes - fixed) / (int64_t)p.stage_bytes);
+    if (capped < 2) capped = 2;
+    if (stages > capped) stages = capped;
+  }
   if (stages > MARCH_MAX_STAGES) stages = MARCH_MAX_STAGES;
   { const char* e = getenv("SCENEEGO_MARCH_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages) stages = atoi(e); }
   p.stages = stages;

@@ -39,10 +39,10 @@ def time_layer(cin, S, B, res, march, env, reps=5, xs=2, pair=2):
 
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-    for cin, res in ((32, True), (32, False), (16, False)):
+    for cin, res in ((32, True), (32, False)):
         us, tf = time_layer(cin, 64, B, res, False, {})
         print(f"conv_tc   {cin}->32 res={int(res)}                         {us:7.1f} us/frame {tf:6.0f} TF", flush=True)
-        envs = [{}, {"SCENEEGO_MARCH_CTAS": "1"}, {"SCENEEGO_MARCH_STAGES": "2"}]
+        envs = [{}, {"SCENEEGO_MARCH_STAGES": "2"}, {}, {"SCENEEGO_MARCH_STAGES": "2"}, {}, {"SCENEEGO_MARCH_STAGES": "2"}]
         for env in envs:
             us, tf = time_layer(cin, 64, B, res, True, env)
             print(f"march     {cin}->32 res={int(res)} {str(env):36s} {us:7.1f} us/frame {tf:6.0f} TF", flush=True)
