@@ -176,10 +176,12 @@ def _pads_clean(dst, lay, S, B):
 
 @pytest.mark.parametrize("cin,cout,S,B,res", [(32, 32, 16, 3, True), (32, 32, 16, 2, False), (16, 32, 16, 2, False),
                                               (32, 32, 32, 5, True), (32, 32, 64, 1, True), (16, 32, 64, 1, False),
-                                              (32, 16, 8, 2, True), (32, 32, 2, 3, True), (32, 32, 40, 2, True)])
+                                              (32, 16, 8, 2, True), (32, 32, 2, 3, True), (32, 32, 40, 2, True),
+                                              (32, 32, 32, 40, True), (16, 32, 32, 70, False)])
 def test_marching_conv(cin, cout, S, B, res):
     """SCENEEGO_OP_CONV3_MARCH (csrc/march.cu): x-marching banded GEMM, resident weights, ring of accumulator
-    slots (B > 1 and S = 40 make the ring wrap at every phase; S = 2 has only face planes)."""
+    slots (B > 1 and S = 40 make the ring wrap at every phase; S = 2 has only face planes; B = 40 / 70 at S = 32 are
+    360 / 630 items on 296 CTAs: whole rounds of interleaved items plus a last round cut by planes)."""
     conv, bn = _mk_conv(cin, cout, 3, seed=31 + cin + S)
     g = torch.Generator().manual_seed(S * 5 + B)
     x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
@@ -208,6 +210,25 @@ def test_marching_conv_fused_shortcut(S, B):
     simt, _, _ = util.run_single_op(t_in, conv, bn, relu=True, impl=1, march=True, shortcut=(sc_conv, sc_bn, x_in))
     assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()
     assert _pads_clean(dst, lay, S, B), "pad / guard cells were written"
+
+
+def test_marching_conv_single_cta_per_sm_variant():
+    """SCENEEGO_MARCH_CTAS=1: one CTA per SM with all 512 TMEM columns (ring of 16 slots, eight epilogue warps) --
+    the configuration the kernel falls back to when resident weights + two stages exceed half an SM."""
+    import os
+    conv, bn = _mk_conv(32, 32, 3, seed=9)
+    g = torch.Generator().manual_seed(4)
+    x = util.bf16_round(torch.randn(3, 32, 24, 24, 24, generator=g)).cuda()
+    r = util.bf16_round(torch.randn(3, 32, 24, 24, 24, generator=g)).cuda()
+    two, _, _ = util.run_single_op(x, conv, bn, relu=True, res=r, impl=0, march=True)
+    os.environ["SCENEEGO_MARCH_CTAS"] = "1"
+    try:
+        one, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=r, impl=0, march=True)
+    finally:
+        del os.environ["SCENEEGO_MARCH_CTAS"]
+    _close(one, _ref(x, conv, bn, True, res=r), "marching conv, one CTA per SM")
+    assert torch.equal(one, two)            # same accumulation order: the ring size does not change the arithmetic
+    assert _pads_clean(dst, lay, 24, 3)
 
 
 def test_marching_conv_is_deterministic_and_reuses_buffers():
