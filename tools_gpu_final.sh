@@ -1,5 +1,5 @@
 #!/bin/bash
-# full GPU test suite (separate processes), smoke, bench (our arm + reference arm)
+# full GPU test suite (separate processes), smoke, bench (our arm + reference arm), launch list
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_info.txt 2>&1
 for f in test_gpu_geometry test_gpu_softargmax test_gpu_eval test_gpu_v2v test_gpu_stage; do
@@ -11,4 +11,6 @@ timeout 900 python bench.py --steps 20 --warmup 3 --profile-ops gpurun_out/v2v_o
 python tools_show_ops.py 2>/dev/null | head -9
 tail -n 3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-cut -c 1-400 gpurun_out/bench_reference.json
+cut -c 1-300 gpurun_out/bench_reference.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
