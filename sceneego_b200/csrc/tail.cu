@@ -138,6 +138,155 @@ __global__ void __launch_bounds__(256, 2) tail_mlp_kernel(const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------
+// tcgen05 variant (default).  The mma.sync kernel above is latency-bound (ncu: issue active 50 %, 16 warps per
+// SM at 128 registers; rolling prefetch, more occupancy and cross-tile interleaving all made it slower), so the
+// chain of three GEMMs moves to the 5th-generation tensor cores with the intermediates staying on the SM:
+//   one CTA per SM = 8 independent groups of 4 warps; a group walks its own 128-position tiles:
+//     TMA (4 planes x 128 cells x 16 B, double-buffered)            -> A tile in shared memory
+//     tcgen05.mma M=128 N=32 K=32 (W1 resident in smem)             -> 32 TMEM columns
+//     tcgen05.ld, + bias, ReLU, bf16 (the unfused chain's rounding) -> the SAME smem tile, now layer 2's A operand
+//     tcgen05.mma N=32 (W2) -> ld / bias / ReLU / bf16 -> smem -> tcgen05.mma N=16 (W3) -> ld, + bias -> f32 logits
+//   The 4 warps of a group are the four TMEM lane quarters; its first lane issues the TMA and the MMAs, a named
+//   barrier per group orders "tile written" before "MMA issued".  Eight groups keep eight such dependent chains
+//   (~2000 cycles each) in flight per SM, which is what hides their latency.
+// ---------------------------------------------------------------------------
+constexpr int TT_GROUPS = 8;
+constexpr int TT_THREADS = TT_GROUPS * 128;
+constexpr uint32_t TT_TILE_BYTES = 4u * 128u * 16u;          // 4 channel-group planes x 128 rows x 16 B
+
+__global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_constant__ TailParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [W1 2048][W2 2048][W3 1024][bias 80 f32 -> 384][barriers 8 groups x 3 x 8 B -> 256][tmem ptr 16]
+  //         then 8 groups x 2 buffers x 8 KB tiles (128-byte aligned)
+  constexpr uint32_t OFF_W1 = 0, OFF_W2 = 2048, OFF_W3 = 4096, OFF_BIAS = 5120, OFF_BAR = 5504, OFF_TMEM = 5760,
+                     OFF_TILES = 5888;
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int grp = warp >> 2, quarter = warp & 3;
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  for (int i = threadIdx.x; i < 5120 / 16; i += TT_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(p.w1)[i];      // w1 | w2 | w3 are contiguous in the blob
+  if (threadIdx.x < 80) s_bias[threadIdx.x] = threadIdx.x < 32 ? p.b1[threadIdx.x] : threadIdx.x < 64 ? p.b2[threadIdx.x - 32] : p.b3[threadIdx.x - 64];
+  auto BAR = [&](int g, int i) { return sbase + OFF_BAR + 8u * (uint32_t)(g * 3 + i); };   // 0,1: TMA full[buf]; 2: MMA done
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < TT_GROUPS; ++g) { mbar_init(BAR(g, 0), 1); mbar_init(BAR(g, 1), 1); mbar_init(BAR(g, 2), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the weights were written with generic stores
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem + (uint32_t)grp * 32u;               // this group's 32 accumulator columns
+  const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t tile0 = sbase + OFF_TILES + (uint32_t)grp * 2u * TT_TILE_BYTES;
+  const bool issuer = (warp & 3) == 0 && lane == 0;
+  const int S = p.ls.side;
+  const size_t N3 = (size_t)S * S * S;
+  const int64_t n_tiles = (p.n_pos + 127) / 128;
+  const int64_t stride = (int64_t)gridDim.x * TT_GROUPS;
+  int64_t tile = (int64_t)blockIdx.x * TT_GROUPS + grp;
+  // descriptors: K-major no-swizzle, SBO = 128 B between 8-row groups, LBO = distance between the two 8-channel chunks
+  constexpr uint32_t DHI = 8u | (1u << 14);
+  auto DESC = [](uint32_t lo) { return ((uint64_t)DHI << 32) | (uint64_t)lo; };
+  constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);
+  constexpr uint32_t ID32 = idesc0 | ((32u >> 3) << 17), ID16 = idesc0 | ((16u >> 3) << 17);
+  const uint32_t a_lbo = (2048u >> 4) << 16;
+  auto load_tile = [&](int64_t t, int buf) {                       // issuer only
+    const uint32_t dst = tile0 + (uint32_t)buf * TT_TILE_BYTES;
+    mbar_expect_tx(BAR(grp, buf), TT_TILE_BYTES);
+    const int64_t q0 = (int64_t)p.ls.guard + t * 128;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      bulk_g2s(dst + (uint32_t)g * 2048u, p.src + ((int64_t)g * p.ls.plane_stride + q0) * 8, 2048u, BAR(grp, buf));
+  };
+  // one layer: A = the group's tile, B = weights at `w_off` with `n` rows; result in the group's TMEM columns
+  auto gemm = [&](uint32_t a_tile, uint32_t w_off, uint32_t n, uint32_t idesc) {   // issuer only
+    const uint32_t a = ((a_tile >> 4) & 0x3FFFu) | a_lbo;
+    const uint32_t b = (((sbase + w_off) >> 4) & 0x3FFFu) | (n << 16);               // LBO = n rows x 16 B
+    tc_mma_bf16(tmem, DESC(a), DESC(b), idesc, 0u);
+    tc_mma_bf16(tmem, DESC(a + (4096u >> 4)), DESC(b + 2u * n), idesc, 1u);          // channels 16..31
+    tc_commit(BAR(grp, 2));
+  };
+  const uint32_t bar_id = 1u + (uint32_t)grp;                        // named barrier of this group (0 = __syncthreads)
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+  // bias + ReLU + bf16 of this row's 32 accumulators -> the row's four 16-byte cells of the tile
+  auto hidden_to_tile = [&](uint32_t a_tile, const float* bias) {
+    uint32_t raw[2][16];
+    tc_ld16(taddr, raw[0]);
+    tc_ld16(taddr + 16u, raw[1]);
+    tc_wait_ld();
+    const uint32_t row = a_tile + (uint32_t)(quarter * 32 + lane) * 16u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(raw[g >> 1][(g & 1) * 8 + j]) + bias[8 * g + j], 0.f);
+      const uint4 v = pack8(o);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + (uint32_t)g * 2048u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
+    tc_fence_before();
+  };
+  if (issuer && tile < n_tiles) load_tile(tile, 0);
+  uint32_t ph_full[2] = {0u, 0u}, ph_mma = 0u;
+  int buf = 0;
+  for (; tile < n_tiles; tile += stride, buf ^= 1) {
+    const uint32_t a_tile = tile0 + (uint32_t)buf * TT_TILE_BYTES;
+    // ---- layer 1
+    if (issuer) {
+      if (tile + stride < n_tiles) load_tile(tile + stride, buf ^ 1);   // that buffer's last reader (an MMA) was awaited
+      mbar_wait(BAR(grp, buf), ph_full[buf]);
+      tc_fence_after();
+      gemm(a_tile, OFF_W1, 32u, ID32);
+    }
+    ph_full[buf] ^= 1u;
+    mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
+    tc_fence_after();
+    hidden_to_tile(a_tile, s_bias);
+    group_sync();
+    // ---- layer 2
+    if (issuer) { tc_fence_after(); gemm(a_tile, OFF_W2, 32u, ID32); }
+    mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
+    tc_fence_after();
+    hidden_to_tile(a_tile, s_bias + 32);
+    group_sync();
+    // ---- layer 3 (16 columns, cout_real of them real)
+    if (issuer) { tc_fence_after(); gemm(a_tile, OFF_W3, 16u, ID16); }
+    mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
+    tc_fence_after();
+    uint32_t raw[16];
+    tc_ld16(taddr, raw);
+    tc_wait_ld();
+    tc_fence_before();
+    group_sync();                                                     // every quarter has read: the next layer 1 may overwrite
+    const uint32_t pos = (uint32_t)((int64_t)p.ls.guard + tile * 128 + quarter * 32 + lane);
+    const uint32_t b = fdiv(pos, p.fd_frame);
+    const int rem = (int)(pos - b * (uint32_t)p.ls.frame_pitch) - p.ls.guard;
+    if ((int)b < p.batch && rem >= 0) {
+      const int x = (int)fdiv((uint32_t)rem, p.fd_px);
+      const int r2 = rem - x * p.ls.pitch_x;
+      const int y = (int)fdiv((uint32_t)r2, p.fd_py);
+      const int z = r2 - y * p.ls.pitch_y;
+      if (x < S && y < S && z < S) {
+        float* o = p.dst + (size_t)b * p.cout_real * N3 + ((size_t)x * S + y) * S + z;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < p.cout_real) __stcs(o + (size_t)c * N3, __uint_as_float(raw[c]) + s_bias[64 + c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"(256u) : "memory");
+}
+
 // CUDA-core checker (op.impl = 1): one thread per voxel, same packed weights, same bf16 roundings.
 __global__ void __launch_bounds__(128) tail_mlp_simt_kernel(const __grid_constant__ TailParams p) {
   const int S = p.ls.side;
@@ -203,11 +352,28 @@ int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
     SE_CUDA_LAUNCH_CHECK("tail_mlp_simt");
     return SCENEEGO_OK;
   }
-  const int64_t n_chunks = (p.n_pos + 63) / 64;
-  int64_t blocks = (n_chunks + 7) / 8;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  tail_mlp_kernel<<<(int)blocks, 256, 0, st>>>(p);
-  SE_CUDA_LAUNCH_CHECK("tail_mlp");
+  if (op.impl == 2) {            // the register-resident mma.sync variant (kept for A/B measurements and tests)
+    const int64_t n_chunks = (p.n_pos + 63) / 64;
+    int64_t blocks = (n_chunks + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    tail_mlp_kernel<<<(int)blocks, 256, 0, st>>>(p);
+    SE_CUDA_LAUNCH_CHECK("tail_mlp");
+    return SCENEEGO_OK;
+  }
+  SE_REQUIRE((const char*)p.w2 == (const char*)p.w1 + 2048 && (const char*)p.w3 == (const char*)p.w1 + 4096 &&
+                 ((uintptr_t)p.w1 & 15) == 0, "v2v_run: op %d: tail weights must be one aligned 5 KB segment", op_index);
+  const size_t smem_bytes = 5888 + (size_t)TT_GROUPS * 2 * TT_TILE_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+    configured = true;
+  }
+  const int64_t n_tiles = (p.n_pos + 127) / 128;
+  int64_t blocks = (n_tiles + TT_GROUPS - 1) / TT_GROUPS;
+  if (blocks > kNumSMs) blocks = kNumSMs;
+  tail_tc_kernel<<<(int)blocks, TT_THREADS, smem_bytes, st>>>(p);
+  SE_CUDA_LAUNCH_CHECK("tail_tc");
   return SCENEEGO_OK;
 }
 

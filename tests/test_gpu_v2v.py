@@ -384,3 +384,31 @@ def test_v2v_simple_vs_reference_golden(mode):
     scale = ref.abs().max().item()
     assert (got - ref).abs().max().item() <= 3e-2 * scale
     assert ((got - ref).norm() / ref.norm()).item() <= 1.5e-2
+
+
+def test_tail_tcgen05_matches_mma_sync_variant():
+    """The fused 1x1 tail on tcgen05 (default, csrc/tail.cu: tail_tc_kernel) vs the register-resident mma.sync
+    variant (op.impl = 2) and the CUDA-core checker: same packed weights, same bf16 roundings of the hidden
+    activations, only the fp32 summation order differs."""
+    from sceneego_b200.network.v2v import V2VModel
+    from sceneego_b200.utils import synth
+    from sceneego_b200 import _lib
+    m = V2VModel(33, 15).eval()
+    sd = synth.synthetic_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=8, mode="random_bn")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    B = 3
+    x = torch.randn(B, 33, 32, 32, 32, generator=torch.Generator().manual_seed(2)).abs().cuda()
+    pg = m.program(32, B, x.device)
+    _lib.pack_volume(x, pg.buffers[pg.in_buf], pg.lay_in)
+    outs = []
+    for impl in (0, 2, 0):
+        o = torch.full((B, 15, 32, 32, 32), float("nan"), device="cuda")
+        m.run_chunk(pg, B, o, impl=impl)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o).all()
+        outs.append(o)
+    assert torch.equal(outs[0], outs[2])                                   # deterministic
+    scale = outs[1].abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 8e-3 * scale          # one bf16 ulp of a hidden activation, propagated
+    assert ((outs[0] - outs[1]).norm() / outs[1].norm()).item() <= 2e-3
