@@ -78,6 +78,7 @@ struct ConvParams {
   int n_dx2;
   uint32_t w_main_bytes;            // bytes of the stencil weights per (half-)blob = offset of the shortcut taps
   int march;                        // checker only: weights in the marching layout [tap(dy,dz)][cin/8][3*n0][8] (march.cu)
+  int n0_shift;                     // log2(n0) when n0 is a power of two (the epilogue's column -> block index), else -1
 };
 
 constexpr int CONV_EPI_WARPS = 8;
@@ -118,7 +119,9 @@ __device__ __forceinline__ RowInfo decode_row(const ConvParams& p, int64_t q64) 
   ri.b = (int)b;
   ri.x = x; ri.y = y; ri.z = z;
   ri.n = (x * S + y) * S + z;
-  ri.dpos = (int64_t)b * p.ld.frame_pitch + p.ld.guard + (int64_t)x * p.ld.pitch_x + (int64_t)y * p.ld.pitch_y + z;
+  // transposed conv: position of output voxel (2x, 2y, 2z); the epilogue adds the parity offset per column block
+  const int m = p.deconv ? 2 : 1;
+  ri.dpos = (int64_t)b * p.ld.frame_pitch + p.ld.guard + (int64_t)(m * x) * p.ld.pitch_x + (int64_t)(m * y) * p.ld.pitch_y + m * z;
   return ri;
 }
 
@@ -498,17 +501,16 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
     // x-stacked ops: column chunk c belongs to output plane x0 + (16c / n0), channels (16c % n0)..+15
     auto shifted = [&](const RowInfo& ri, int x0, int c, int& ch0) -> RowInfo {
       if (XS == 1 && p.deconv) {
-        const int blk = (c << 4) / p.n0;
+        const int blk = p.n0_shift >= 0 ? ((c << 4) >> p.n0_shift) : (c << 4) / p.n0;
         const int par = p.par0 + blk;
         ch0 = (c << 4) - blk * p.n0;
         RowInfo r = ri;
         r.write = ri.valid;                                  // pads of the 2x volume are never touched
-        r.dpos = (int64_t)ri.b * p.ld.frame_pitch + p.ld.guard + (int64_t)(2 * ri.x + (par >> 2)) * p.ld.pitch_x +
-                 (int64_t)(2 * ri.y + ((par >> 1) & 1)) * p.ld.pitch_y + (2 * ri.z + (par & 1));
+        r.dpos = ri.dpos + ((par >> 2) * p.ld.pitch_x + ((par >> 1) & 1) * p.ld.pitch_y + (par & 1));
         return r;
       }
       if (XS == 1) { ch0 = c << 4; return ri; }
-      const int sft = (c << 4) / p.n0;
+      const int sft = p.n0_shift >= 0 ? ((c << 4) >> p.n0_shift) : (c << 4) / p.n0;
       ch0 = (c << 4) - sft * p.n0;
       RowInfo r = ri;
       const bool in = (x0 + sft) < S;
@@ -927,6 +929,8 @@ extern "C" int sceneego_v2v_pack_conv(const float* h_weight, const float* h_bias
 }
 
 static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t st) {
+  p.n0_shift = -1;
+  for (int k = 3; k < 10; ++k) if ((1 << k) == p.n0) p.n0_shift = k;
   const int64_t n_pos = (int64_t)batch * p.ls.frame_pitch;
   // fdiv() is exact while n * d < 2^48 and n fits 32 bits
   SE_REQUIRE(n_pos + 4096 < (1ll << 31) && (n_pos + 4096) * (int64_t)p.ls.frame_pitch < (1ll << 48),
