@@ -163,13 +163,16 @@ class VoxelNetwork_depth(nn.Module):
             # returned tensor is therefore overwritten by the next call (clone it to keep it); consumers on the
             # current stream are ordered after the writer, and the next call's writer after them.
             shape = (b, 32, self.image_height, self.image_width)
-            if self._features_buf is None or tuple(self._features_buf.shape) != shape:
-                self._features_buf = None
-                self._features_buf = torch.empty(shape, dtype=torch.float32, device=feat.device)
+            if self._features_buf is None:
+                self._features_buf = {}
+            if b not in self._features_buf:
+                if len(self._features_buf) >= 4:            # a few batch sizes at most (e.g. the pipeline's ramp-up)
+                    self._features_buf.clear()
+                self._features_buf[b] = torch.empty(shape, dtype=torch.float32, device=feat.device)
             with torch.cuda.stream(side):
                 features = _lib.features_upsample_pad(feat32, self.image_height,
                                                       (self.image_width - self.image_height) // 2,
-                                                      out=self._features_buf)
+                                                      out=self._features_buf[b])
                 feat_done = torch.cuda.Event()
                 feat_done.record(side)
             feat32.record_stream(side)

@@ -173,3 +173,27 @@ def test_with_intersection_vs_reference(tables64, mode):
     assert torch.equal(x[0, 32:64], x[0, :32] * occ)
     with pytest.raises(_lib.SceneEgoError):             # the reference's scene_volumes path feeds 33 channels to this net
         net.lift(feat.cuda(), net.grid_coord_proj_batch, net.coord_volumes, scene_volumes=occ[None])
+
+
+def test_host_pipeline_matches_direct_lift(net, tables64):
+    """HostStagePipeline.run (pinned host buffers -> poses on the host; the first batch of a call is ramped through
+    the copy stream in parts) returns exactly what lift() returns on the same frames, for ramped and plain batches."""
+    from sceneego_b200.pipeline import HostStagePipeline
+    _load(net, "random_bn", 1.0)
+    B = 8
+    feats = [synth.synthetic_features(B, seed=40 + i).pin_memory() for i in range(3)]
+    depths = [synth.synthetic_depth_room(B, tables64.ray, seed=50 + i).pin_memory() for i in range(3)]
+    pipe = HostStagePipeline(net)
+    pipe.ramp_min_batch = 8                                  # ramp already at this small test batch: parts of 2, 2, 4 frames
+    outs = [o.clone() for o in pipe.run(list(zip(feats, depths)))]
+    assert pipe.h2d_bytes == sum(f.numel() * 4 + d.numel() * 4 for f, d in zip(feats, depths)) and pipe.d2h_bytes == 3 * B * 15 * 3 * 4
+    again = [o.clone() for o in pipe.run(list(zip(feats, depths)))]          # buffers reused, same results
+    with torch.no_grad():
+        for i in range(3):
+            ref = net.lift(feats[i].cuda(), net.grid_coord_proj_batch, net.coord_volumes, depth_map_batch=depths[i].cuda())[0].cpu()
+            # no cross-frame state: cutting the batch only changes how many partial sums the soft-argmax splits a
+            # joint volume into (fp32 summation order): 1e-6 m
+            assert torch.equal(outs[i], again[i]), i
+            assert (outs[i] - ref).abs().max().item() <= 1e-6, i
+    with pytest.raises(ValueError):
+        pipe.run([(feats[0].clone(), depths[0])])            # pageable host memory is refused
