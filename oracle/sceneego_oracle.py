@@ -6,8 +6,9 @@ module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 timed CPU baseline -- never as the product path.
 
 It restates, in NumPy / CPU-torch, the algorithm of the reference hot path
-(``/root/reference/network/voxel_net_depth.py:237-273``).  Each function cites
-the reference lines it follows.  Parity pin: the reference ships no tests or
+(``/root/reference/network/voxel_net_depth.py:237-273``) and of the callers either
+side of it that the product also covers (dataset depth preprocessing, ``V2VModelSimple``,
+the MPJPE / PA-MPJPE evaluation).  Each function cites the reference lines it follows.  Parity pin: the reference ships no tests or
 golden vectors, so this oracle is pinned against outputs
 of the unmodified reference imported in the build container -- see
 ``tests/make_golden.py`` (generator) and ``tests/golden/*.npz`` (committed
