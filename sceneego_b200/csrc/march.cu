@@ -13,8 +13,9 @@
 //   * the whole weight array (27 taps: 55 KB for 32 -> 32) stays RESIDENT in shared memory -- no weight stream;
 //   * accumulators are a RING of 512/Cout tensor-memory slots, one output plane each: output p is complete
 //     when plane p+1 has been issued, its slot is committed to the epilogue and recycled 16 planes later.
-//     Where the three slots of a band straddle the end of the ring the MMA is split in two (2 of 16 planes);
-//     the first MMA of a plane is split so that the newly opened slot is overwritten, not accumulated.
+//     Where the three slots of a band straddle the end of the ring the MMA is split in two (2 planes per ring
+//     revolution); every MMA accumulates -- the epilogue hands a drained slot back cleared (tcgen05.st of zeros),
+//     so the slot a plane opens needs no overwriting MMA of its own.
 //   warp 0 = producer (cp.async.bulk of one (cin/8)-plane window per input plane, 2..8-stage ring)
 //   warp 1 = TMEM allocator + the one MMA issuer (an N = 96 MMA takes longer than the 41.5-cycle issue floor)
 //   then 4 or 8 epilogue warps: one or two per TMEM lane quarter (two alternate output planes); row decode
@@ -96,6 +97,15 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
+  // every accumulator slot starts cleared: all MMAs accumulate, and the epilogue re-clears a slot after draining it
+  if (warp >= 2 && warp < 6) {                       // four warps = the four TMEM lane quarters
+    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (uint32_t c = 0; c < TMEM_COLS; c += 16) tc_st16_zero(t0 + c);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   // Work split.  Whole rounds: CTA k marches items k, k + grid, ... -- neighbouring CTAs work on neighbouring
   // tiles of the same frame at the same plane at the same time, so the halo cells two tiles share are read from
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
         // band: row block j of the weight array feeds output xi - 1 + j, kept to the outputs of this march
         const int j_lo = xi - 1 >= x0 ? 0 : (xi >= x0 ? 1 : 2);
         const int j_hi = xi + 1 < x1 ? 2 : (xi < x1 ? 1 : 0);
-        const int jf = (xi == xa && xa == x0) ? 1 : 2;          // first block this plane OPENS (overwrites)
+        const int jf = (xi == xa && xa == x0) ? 1 : 2;          // first block this plane OPENS (the epilogue cleared it)
         const uint32_t gj0 = G + (uint32_t)(xi - x0) - 1u;      // running index of block 0's output
         for (int j = jf > j_lo ? jf : j_lo; j <= j_hi; ++j)      // the epilogue has drained the slots this plane opens
           mbar_wait_warp(BAR(B_ACC_EMPTY + (int)SLOT(gj0 + (uint32_t)j)), PAR(gj0 + (uint32_t)j) ^ 1u);
@@ -230,16 +240,10 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
           const uint32_t dA = tmem_u + sA * N0, dB = tmem_u;
           const uint32_t bA = w_b + (uint32_t)(j_lo * N0), bB = w_b + (uint32_t)((j_lo + nA) * N0);
           auto IDN = [&](int n) { return ID1 + (uint32_t)(n - 1) * ((uint32_t)(N0 >> 3) << 17); };
-          // first MMA of the plane, split so that opened slots are overwritten and open ones accumulated
-          auto FIRST = [&](int ja, int n, uint32_t d, uint32_t bb) {
-            int na = jf - ja; na = na < 0 ? 0 : (na > n ? n : na);
-            if (na > 0) tc_mma_bf16(d, DESC(a0), DESC(bb), IDN(na), 1u);
-            if (n - na > 0) tc_mma_bf16(d + (uint32_t)(na * N0), DESC(a0), DESC(bb + (uint32_t)(na * N0)), IDN(n - na), 0u);
-          };
-          FIRST(j_lo, nA, dA, bA);
-          if (nB > 0) FIRST(j_lo + nA, nB, dB, bB);
-          RUN(a0, bA, dA, IDN(nA), 1u, true);
-          if (nB > 0) RUN(a0, bB, dB, IDN(nB), 1u, true);
+          // every MMA accumulates: the epilogue leaves a drained slot cleared (tcgen05.st of zeros), so the slot a
+          // plane opens needs no overwriting first MMA of its own (the N = 64 + N = 32 split cost 33 cycles per plane)
+          RUN(a0, bA, dA, IDN(nA), 1u, false);
+          if (nB > 0) RUN(a0, bB, dB, IDN(nB), 1u, false);
           if constexpr (KSTEPS2 > 0) {
             // fused 1x1 shortcut: the plane's own output, from the halo-free window of the second source
             if (xi >= x0 && xi < x1) {
@@ -304,6 +308,9 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tc_ld16(taddr + (uint32_t)(16 * c), raw[c]);
         tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tc_st16_zero(taddr + (uint32_t)(16 * c));    // hand the slot back cleared
+        tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + slot));
