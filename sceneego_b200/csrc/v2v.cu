@@ -844,10 +844,26 @@ static bool try_plan(ConvParams& p, int tiles, int want_stages) {
   return true;
 }
 
-static int plan_conv(ConvParams& p) {
+static int plan_conv(ConvParams& p, int64_t n_pos) {
   p.tap_bytes = (uint32_t)p.cin_planes * (p.mma_n / p.cg) * 16u;   // per CTA; mma_n includes the x-stacking factor
   int max_tiles = 256 / p.N;
   if (max_tiles > 8) max_tiles = 8;
+  // the deep, small levels (S <= 8 at 64 frames) have fewer work items than SMs: smaller items put more CTAs to
+  // work on them (each streams the whole weight array anyway; what counts there is latency, not reuse)
+  // and while there are only a few rounds of items, the tile count with the fewest (rounds x tiles) wins: 175 two-tile
+  // items are two rounds on 148 SMs, 350 one-tile items three rounds of half the length
+  if (p.xs == 1 && p.cg == 1) {
+    auto items_of = [&](int t) { return (n_pos + (int64_t)t * 128 - 1) / ((int64_t)t * 128); };
+    if (items_of(max_tiles) < 4 * kNumSMs) {
+      int best = max_tiles;
+      int64_t best_cost = ((items_of(max_tiles) + kNumSMs - 1) / kNumSMs) * max_tiles;
+      for (int t = max_tiles >> 1; t >= 1; t >>= 1) {
+        const int64_t cost = ((items_of(t) + kNumSMs - 1) / kNumSMs) * t;
+        if (cost < best_cost) { best_cost = cost; best = t; }
+      }
+      max_tiles = best;
+    }
+  }
   const char* et = getenv("SCENEEGO_TILES");
   const char* es = getenv("SCENEEGO_STAGES");
   if (et || es) {
@@ -938,7 +954,7 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
   p.fd_frame = make_fastdiv((uint32_t)p.ls.frame_pitch);
   p.fd_px = make_fastdiv((uint32_t)p.ls.pitch_x);
   p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
-  const int smem = plan_conv(p);
+  const int smem = plan_conv(p, n_pos);
   SE_REQUIRE(smem > 0, "v2v_run: op %d does not fit shared memory", op_index);
   if (p.xs == 1) {
     p.n_items = (int)((n_pos + p.L - 1) / p.L);
