@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_con
     const uint32_t a_tile = tile0 + (uint32_t)buf * TT_TILE_BYTES;
     // ---- layer 1
     if (issuer) {
-      if (tile + stride < n_tiles) load_tile(tile + stride, buf ^ 1);   // that buffer's last reader (an MMA) was awaited
       mbar_wait(BAR(grp, buf), ph_full[buf]);
       tc_fence_after();
       gemm(a_tile, OFF_W1, 32u, ID32);
+      if (tile + stride < n_tiles) load_tile(tile + stride, buf ^ 1);   // that buffer's last reader (an MMA) was awaited
     }
     ph_full[buf] ^= 1u;
     mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
