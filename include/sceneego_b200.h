@@ -183,7 +183,8 @@ int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_layout_t* la
 enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2,
        SCENEEGO_OP_STEM7_S2D = 3,  /* Conv3d(33,16,k7)+BN+ReLU from an s2d source, network/v2v.py:147 */
        SCENEEGO_OP_TAIL_MLP = 4    /* back_layers[1], back_layers[2] and output_layer (three 1x1 convs,
-                                      network/v2v.py:150-161,168-169) in one pass; blob segment at w_offset:
+                                      network/v2v.py:150-161,168-169) in one pass (three chained tcgen05 GEMMs per
+                                      128-voxel tile, hidden activations in shared memory); blob segment at w_offset:
                                       [w1 32x32][w2 32x32][w3 32x16] bf16 (pack_conv layout), then
                                       [b1 32][b2 32][b3 16] f32; dst = (B,cout_real,S,S,S) f32 */,
        SCENEEGO_OP_CONV3_MARCH = 5 /* Conv3d k3 + folded BN (+ residual / ReLU / fused projection shortcut) with
@@ -209,7 +210,8 @@ typedef struct sceneego_v2v_op {
   int32_t cout;        /* padded to a multiple of 16                                       */
   int32_t cout_real;   /* channels actually written (15 for the output layer)             */
   int32_t src, dst, res;  /* buffer indices (res = -1 if unused)                           */
-  int32_t impl;        /* 0 = tcgen05 implicit GEMM, 1 = CUDA-core checker kernel          */
+  int32_t impl;        /* 0 = tcgen05 kernels, 1 = CUDA-core checker kernel, 2 = (TAIL_MLP only)
+                          the register-resident mma.sync variant; other ops treat 2 like 0  */
   int32_t xstack;      /* conv: GEMM rows produce `xstack` consecutive x-planes (N = xstack*cout),
                           weights packed with the same xstack; 0/1 = off                    */
   int32_t cta_pair;    /* conv: 2 = run on CTA pairs (tcgen05 cta_group::2, M = 256); weights packed
