@@ -251,10 +251,10 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
                                                        int img_h, int img_w, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16,
                                                        sceneego_vol_layout_t lay, int extra_zero_planes,
-                                                       int up_shift_y, int up_shift_x, int log2v) {
+                                                       int up_shift_y, int up_shift_x, int log2v, int batch,
+                                                       int frames_per_thread) {
   constexpr int C = 32;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
   const int N = V * V * V;
   if (n >= N) return;
   // power-of-two sides: shifts instead of runtime integer divisions
@@ -279,10 +279,6 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
   const int x0 = (int)x0f, y0 = (int)y0f;
   const int pad = (img_w - img_h) / 2;
 
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
-  const float* fb = feat + (size_t)b * h * w * C;
   // The image plane is the 16x nearest-upsampled source, so the four bilinear taps usually (88 % of the
   // voxels at V = 64) fall into ONE source cell: taps are merged per source cell and each distinct
   // 128-byte cell is fetched once (the gather is L2-bandwidth-bound otherwise).
@@ -309,6 +305,13 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < t; ++u)
       if (cell[t] >= 0 && cell[t] == cell[u]) { wt[u] += wt[t]; cell[t] = -1; }
+  // the voxel's geometry (projection, taps, weights) is frame-invariant: it is computed once and applied to
+  // `frames_per_thread` frames (it was two thirds of the kernel's instructions when every frame recomputed it)
+  for (int b = blockIdx.y * frames_per_thread; b < min(batch, (int)(blockIdx.y + 1) * frames_per_thread); ++b) {
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  const float* fb = feat + (size_t)b * h * w * C;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     if (cell[t] >= 0) {
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
         *reinterpret_cast<uint4*>(out_bf16 + (cell0 + (int64_t)g * lay.plane_stride) * 8) = make_uint4(0, 0, 0, 0);
     }
   }
+  }   // frames
 }
 
 // ---------------------------------------------------------------------------
@@ -605,7 +609,8 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
   SE_REQUIRE(!d_out_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V), "unproject: bf16 output needs a matching layout");
   SE_REQUIRE(batch > 0 && batch <= 65535 && img_w >= img_h, "unproject: bad batch / image plane");
   const int N = V * V * V;
-  dim3 grid((N + 127) / 128, batch);
+  const int fpt = batch >= 32 ? 4 : batch >= 8 ? 2 : 1;       // frames per thread (grid.y stays >= 8 blocks deep)
+  dim3 grid((N + 127) / 128, (batch + fpt - 1) / fpt);
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
   const float step = (float)((double)side / (V - 1));
   const float lo = (float)(-(double)side / 2);
@@ -621,11 +626,11 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
   if (d_grid)
     unproject_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, d_grid, cam, h, w, V, lo, step, img_h,
                                                                     img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
-                                                                    extra_zero_planes, sh_y, sh_x, log2v);
+                                                                    extra_zero_planes, sh_y, sh_x, log2v, batch, fpt);
   else
     unproject_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(d_feat, nullptr, cam, h, w, V, lo, step, img_h,
                                                                    img_w, d_out_f32, (__nv_bfloat16*)d_out_bf16, L,
-                                                                   extra_zero_planes, sh_y, sh_x, log2v);
+                                                                   extra_zero_planes, sh_y, sh_x, log2v, batch, fpt);
   SE_CUDA_LAUNCH_CHECK("unproject");
   return SCENEEGO_OK;
 }
