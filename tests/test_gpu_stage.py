@@ -197,3 +197,23 @@ def test_host_pipeline_matches_direct_lift(net, tables64):
             assert (outs[i] - ref).abs().max().item() <= 1e-6, i
     with pytest.raises(ValueError):
         pipe.run([(feats[0].clone(), depths[0])])            # pageable host memory is refused
+
+
+def test_lift_with_fused_depth_preprocessing(net, tables64):
+    """net.depth_preprocess = (1024, 1280, 10.0): depth_map_batch holds the RAW decoded maps (512x640 demo EXRs, values
+    above 10 m) and the dataset's resize + clamp (dataset/demo_dataset.py:86-91) happen inside the voxelisation kernel.
+    Same poses, bit for bit, as preprocessing on the host first."""
+    _load(net, "random_bn", 1.0)
+    g = util.golden("voxel.npz")
+    raws = np.stack([g[f"{n}_raw"] for n in ("img_001000", "img_001796", "img_002376")]).astype(np.float32)
+    raws[1, 100:140, 200:260] = 25.0                                     # beyond the clamp
+    pre = np.stack([orc.preprocess_depth(r) for r in raws])
+    feat = synth.synthetic_features(3, seed=9).cuda()
+    with torch.no_grad():
+        a = net.lift(feat, net.grid_coord_proj_batch, net.coord_volumes, depth_map_batch=torch.from_numpy(pre).cuda())[0]
+        net.depth_preprocess = (1024, 1280, 10.0)
+        try:
+            b = net.lift(feat, net.grid_coord_proj_batch, net.coord_volumes, depth_map_batch=torch.from_numpy(raws).cuda())[0]
+        finally:
+            net.depth_preprocess = None
+    assert torch.equal(a, b)
