@@ -1,7 +1,7 @@
 #!/bin/bash
 # tests + smoke + bench + ncu evidence, one box lease
 mkdir -p gpurun_out
-./tools_gpu_tests.sh > gpurun_out/tests_summary.txt 2>&1
+./tools/gpu_tests.sh > gpurun_out/tests_summary.txt 2>&1
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 900 python bench.py --steps 10 --warmup 3 --profile-ops gpurun_out/v2v_ops.json > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err

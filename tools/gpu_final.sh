@@ -8,7 +8,7 @@ for f in test_gpu_geometry test_gpu_softargmax test_gpu_eval test_gpu_v2v test_g
 done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -n 1 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 20 --warmup 3 --profile-ops gpurun_out/v2v_ops.json > gpurun_out/bench.json 2> gpurun_out/bench.err
-python tools_show_ops.py 2>/dev/null | head -9
+python tools/show_ops.py 2>/dev/null | head -9
 tail -n 3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 cut -c 1-300 gpurun_out/bench_reference.json

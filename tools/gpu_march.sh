@@ -9,4 +9,4 @@ tail -n 6 gpurun_out/quick_tests.log
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-ops gpurun_out/v2v_ops.json > gpurun_out/bench.json 2> gpurun_out/bench.err
 cut -c 1-300 gpurun_out/bench.json
 tail -n 5 gpurun_out/bench.err
-python tools_show_ops.py gpurun_out/v2v_ops.json 2>/dev/null | head -70
+python tools/show_ops.py gpurun_out/v2v_ops.json 2>/dev/null | head -70
