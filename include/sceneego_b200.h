@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCENEEGO_ABI_VERSION 3
+#define SCENEEGO_ABI_VERSION 4
 
 enum {
   SCENEEGO_OK = 0,
@@ -157,14 +157,24 @@ int sceneego_voxelize_depth_f64(const float* d_depth, int batch, int h, int w, c
 /* Same, with the DATASET's preprocessing of the raw depth map fused into the load:
  * replaces cv2.resize(depth, (pre_w, pre_h), INTER_NEAREST) when the raw map is not pre_h x pre_w, and
  * depth_map[depth_map > clamp_max] = clamp_max (dataset/demo_dataset.py:86-91, dataset/test_dataset.py:138-143),
- * followed by sceneego_voxelize_depth_f64 on the result; with d_occ_f32 it is also the voxel_output=True path
- * depth_map_to_voxel (dataset/real_depth_utils.py:29-60).  Nearest indices are OpenCV's:
+ * followed by sceneego_voxelize_depth_f64 on the result (the NETWORK's voxelisation: squash to img_h x img_h, pad).
+ * Nearest indices are OpenCV's:
  * min(cvFloor(dst * (1. / ((double)n_dst / n_src))), n_src - 1).  clamp_max = +inf disables the clamp.
  *   d_depth_raw (B,h,w) f32 as decoded from the EXR (first channel) */
 int sceneego_voxelize_depth_raw_f64(const float* d_depth_raw, int batch, int h, int w, int pre_h, int pre_w,
                                     float clamp_max, const double* d_ray, int img_h, int img_w, int volume_size,
                                     double cuboid_side, float* d_occ_f32, void* d_occ_bf16,
                                     const sceneego_vol_layout_t* lay, int channel, void* stream);
+
+/* The DATASET's voxelisation -- replaces depth_map_to_voxel / point_cloud_to_voxel_pytorch
+ * (dataset/real_depth_utils.py:29-60), the voxel_output=True path of dataset/demo_dataset.py:93-94 and
+ * dataset/test_dataset.py:145-146.  Unlike the network's, the preprocessed (pre_h, pre_w) map is multiplied by the
+ * (pre_h, pre_w) ray table pixel for pixel: no squash to H x H, no zero-padded columns.  The dataset's resize of the
+ * raw (h,w) map to (pre_h, pre_w) and its clamp are fused into the load as above.
+ *   d_ray (pre_h, pre_w, 3) fp64 row-major;  d_occ_f32 (B,V,V,V) f32, zero-initialised by the caller */
+int sceneego_voxelize_depth_dataset_f64(const float* d_depth_raw, int batch, int h, int w, int pre_h, int pre_w,
+                                        float clamp_max, const double* d_ray, int volume_size, double cuboid_side,
+                                        float* d_occ_f32, void* stream);
 
 /* with_intersection (network/voxel_net_depth.py:257-260): volumes = cat([volumes, volumes * scene, scene]).
  * In place on a plain planar bf16 volume whose channels [0,c) hold the lifted features and channel 2c the
@@ -289,13 +299,14 @@ int sceneego_softargmax3d_f32(const float* d_logits, int batch, int joints, int 
 /* The metric loop of test.py (dataset/test_dataset.py:102-112) for a batch of poses: replaces calculate_error
  * (utils/calculate_errors.py:22-28), align_skeleton(estimated, gt, None, scale) (:60-91) and umeyama
  * (utils/rigid_transform_with_scale.py:18-43).  fp64 like the reference's NumPy.
- *   d_pred (B,J,3) f32 network output;  d_gt (B,J,3) f64
+ *   d_pred (B,J,3) network output, f32 (pred_is_f64 == 0) or f64 (the reference keeps the caller's dtype: float32
+ *           predictions are promoted element by element, float64 ones used as they are);  d_gt (B,J,3) f64
  *   d_mpjpe[B], d_pampjpe[B]: per-frame mean joint distance before / after the per-frame similarity alignment
  *                             (their means over B are the two numbers test.py prints); either may be NULL
  *   d_aligned (B,J,3) f64 aligned poses, d_gt_out (B,J,3) f64 the ground truth align_skeleton returns
  *                             (centred when scale == 0), d_transform (B,13) f64 = c, R row-major, t; any may be NULL
  *   scale: 1 = pose.dot(R) * c + t;  0 = centre both poses first, pose.dot(R) + t */
-int sceneego_pose_errors_f64(const float* d_pred, const double* d_gt, int batch, int joints, int scale,
+int sceneego_pose_errors_f64(const void* d_pred, int pred_is_f64, const double* d_gt, int batch, int joints, int scale,
                              double* d_mpjpe, double* d_pampjpe, double* d_aligned, double* d_gt_out,
                              double* d_transform, void* stream);
 

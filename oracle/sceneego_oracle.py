@@ -224,6 +224,29 @@ def voxelize_depth(depth: np.ndarray, ray: np.ndarray, volume_size: int, cuboid_
     return vox
 
 
+def voxelize_depth_dataset(depth: np.ndarray, ray: np.ndarray, volume_size: int, cuboid_side: float) -> np.ndarray:
+    """dataset/real_depth_utils.py:29-60 (`depth_map_to_voxel` + `point_cloud_to_voxel_pytorch`), the function the
+    datasets call with `voxel_output=True` (dataset/demo_dataset.py:93-94, dataset/test_dataset.py:145-146).
+
+    NOT the network's `depth_map_to_voxel_numpy`: the preprocessed (image_height, image_width) map is multiplied by
+    the ray table pixel for pixel -- no nearest squash to H x H and no zero-padded columns (:31-33).  The
+    quantisation (:46-56) is the same as voxel_net_depth.py:207-222.
+    """
+    V, s = volume_size, cuboid_side
+    flat = np.asarray(depth, dtype=np.float32).T.reshape(-1)   # index x*H + y, like the x-major ray table
+    pc = (ray.T * flat).T                                       # fp64
+    q = np.empty_like(pc)
+    q[:, 0] = (pc[:, 0] + s / 2) * V / s
+    q[:, 1] = (pc[:, 1] + s / 2) * V / s
+    q[:, 2] = pc[:, 2] * V / s
+    q = np.round(q)
+    ok = np.all(np.logical_and(V - 1 >= q, q >= 0), axis=1)
+    qi = q[ok].astype(np.int64)
+    vox = np.zeros((V, V, V), dtype=np.float32)
+    vox[qi[:, 0], qi[:, 1], qi[:, 2]] = 1.0
+    return vox
+
+
 # ----------------------------------------------------------------------------
 # a7: V2V encoder-decoder (network/v2v.py), functional, fp32
 # ----------------------------------------------------------------------------

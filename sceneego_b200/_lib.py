@@ -23,6 +23,7 @@ SYMBOLS = [
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
     "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16", "sceneego_pose_errors_f64",
+    "sceneego_voxelize_depth_dataset_f64",
 ]
 
 
@@ -71,7 +72,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sceneego_vol_layout_make_s2d.restype = C.c_int64
     lib.sceneego_v2v_stem_s2d_weight_bytes.restype = C.c_size_t
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
-    if lib.sceneego_abi_version() != 3:
+    if lib.sceneego_abi_version() != 4:
         raise SceneEgoError("libsceneego_b200.so ABI version mismatch")
     if path is None:
         _lib = lib
@@ -86,18 +87,62 @@ def _check(rc: int, what: str) -> None:
         raise SceneEgoError(f"{what} failed (code {rc}): {msg}")
 
 
-def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+def _ptr(t: Optional[torch.Tensor], device: Optional[torch.device] = None) -> C.c_void_p:
     if t is None:
         return C.c_void_p(0)
     if not t.is_cuda:
         raise SceneEgoError("sceneego_b200 ops need CUDA tensors (no CPU fallback)")
+    if device is not None and t.device != device:
+        raise SceneEgoError(f"sceneego_b200 op: tensors on different devices ({t.device} vs {device})")
     if not t.is_contiguous():
         raise SceneEgoError("sceneego_b200 ops need contiguous tensors")
     return C.c_void_p(t.data_ptr())
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _as_device(device) -> torch.device:
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise SceneEgoError("sceneego_b200 ops need a CUDA device (no CPU fallback)")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+class on_device:
+    """Make `device` the current CUDA device for the duration of a C-ABI call.  The library never calls
+    cudaSetDevice: kernels launch on the calling thread's current device, so the binding selects the device the
+    tensors live on (a module built with device='cuda:1' works without torch.cuda.set_device(1))."""
+
+    def __init__(self, device):
+        self.device = _as_device(device)
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.device.index:
+            self.prev = cur
+            torch.cuda.set_device(self.device.index)
+        return self.device
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _stream(device=None) -> C.c_void_p:
+    """torch's current stream ON THE GIVEN DEVICE (a tensor or a device; default: the current device)."""
+    if isinstance(device, torch.Tensor):
+        device = device.device
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _call(name: str, anchor, *args) -> None:
+    """lib.<name>(*args, stream): `anchor` (tensor or device) fixes the device and the stream; tensor arguments become
+    raw pointers after a same-device / contiguity check, None becomes NULL."""
+    dev = _as_device(anchor.device if isinstance(anchor, torch.Tensor) else anchor)
+    conv = [_ptr(a, dev) if isinstance(a, torch.Tensor) else a for a in args]
+    with on_device(dev):
+        rc = getattr(load_library(), name)(*conv, _stream(dev))
+    _check(rc, name.replace("sceneego_", ""))
 
 
 def make_calib(cx, cy, c2w, w2c, width, height) -> Calib:
@@ -136,19 +181,20 @@ def alloc_volume(lay: VolLayout, channels: int, device) -> torch.Tensor:
 
 # ---- thin per-op wrappers (argument checking lives in C) ---------------------
 def ray_table(calib: Calib, device) -> torch.Tensor:
+    device = _as_device(device)
     out = torch.empty(calib.height, calib.width, 3, dtype=torch.float64, device=device)
-    _check(load_library().sceneego_ray_table_f64(C.byref(calib), _ptr(out), _stream()), "ray_table")
+    _call("sceneego_ray_table_f64", out, C.byref(calib), out)
     return out
 
 
 def project_voxels(calib: Calib, volume_size: int, cuboid_side: float, heatmap_shape, device):
+    device = _as_device(device)
     n = volume_size ** 3
     px = torch.empty(n, 2, dtype=torch.float32, device=device)
     grid = torch.empty(n, 2, dtype=torch.float32, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    _check(load_library().sceneego_project_voxels_f32(
-        C.byref(calib), int(volume_size), C.c_float(cuboid_side), int(heatmap_shape[0]), int(heatmap_shape[1]),
-        _ptr(px), _ptr(grid), _ptr(status), _stream()), "project_voxels")
+    _call("sceneego_project_voxels_f32", px, C.byref(calib), int(volume_size), C.c_float(cuboid_side),
+          int(heatmap_shape[0]), int(heatmap_shape[1]), px, grid, status)
     if int(status.item()) != 0:
         raise Exception("norm is zero!")
     return px, grid
@@ -158,8 +204,7 @@ def world2camera(calib: Calib, points: torch.Tensor) -> torch.Tensor:
     n = points.shape[0]
     px = torch.empty(n, 2, dtype=torch.float32, device=points.device)
     status = torch.zeros(1, dtype=torch.int32, device=points.device)
-    _check(load_library().sceneego_world2camera_f32(C.byref(calib), _ptr(points), n, _ptr(px), _ptr(status),
-                                                    _stream()), "world2camera")
+    _call("sceneego_world2camera_f32", points, C.byref(calib), points, n, px, status)
     if int(status.item()) != 0:
         raise Exception("norm is zero!")
     return px
@@ -168,20 +213,23 @@ def world2camera(calib: Calib, points: torch.Tensor) -> torch.Tensor:
 def grid_sample(img: torch.Tensor, grid: torch.Tensor, grid_batch_stride: int) -> torch.Tensor:
     b, c, h, w = img.shape
     n = grid.shape[-3] if grid.dim() == 4 else grid.shape[0]
+    if grid.device != img.device:
+        raise SceneEgoError("grid_sample: image and grid on different devices")
     out = torch.empty(b, c, n, dtype=torch.float32, device=img.device)
-    _check(load_library().sceneego_grid_sample_f32(_ptr(img), C.c_void_p(grid.data_ptr()),
-                                                   C.c_int64(grid_batch_stride), b, c, h, w, n, _ptr(out),
-                                                   _stream()), "grid_sample")
+    _call("sceneego_grid_sample_f32", img, img, C.c_void_p(grid.data_ptr()), C.c_int64(grid_batch_stride), b, c, h, w,
+          n, out)
     return out
 
 
-def feature_conv1x1(feat: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+def feature_conv1x1(feat: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     b, cin, h, w = feat.shape
     cout = weight.shape[0]
-    out = torch.empty(b, h, w, cout, dtype=torch.float32, device=feat.device)
-    _check(load_library().sceneego_feature_conv1x1_f32(
-        _ptr(feat), _ptr(weight.reshape(cout, cin)), _ptr(bias), _ptr(out), b, cin, cout, h, w, _stream()),
-        "feature_conv1x1")
+    if out is None:
+        out = torch.empty(b, h, w, cout, dtype=torch.float32, device=feat.device)
+    elif tuple(out.shape) != (b, h, w, cout) or out.dtype != torch.float32:
+        raise SceneEgoError("feature_conv1x1: bad output buffer")
+    _call("sceneego_feature_conv1x1_f32", feat, feat, weight.reshape(cout, cin), bias, out, b, cin, cout, h, w)
     return out
 
 
@@ -191,8 +239,7 @@ def features_upsample_pad(feat_cl: torch.Tensor, up: int, pad: int, out: Optiona
         out = torch.empty(b, c, up, up + 2 * pad, dtype=torch.float32, device=feat_cl.device)
     elif tuple(out.shape) != (b, c, up, up + 2 * pad) or out.dtype != torch.float32 or not out.is_contiguous():
         raise SceneEgoError("features_upsample_pad: bad output buffer")
-    _check(load_library().sceneego_features_upsample_pad_f32(_ptr(feat_cl), _ptr(out), b, c, h, w, up, pad,
-                                                              _stream()), "features_upsample_pad")
+    _call("sceneego_features_upsample_pad_f32", feat_cl, feat_cl, out, b, c, h, w, up, pad)
     return out
 
 
@@ -200,78 +247,86 @@ def unproject(feat_cl: torch.Tensor, grid: Optional[torch.Tensor], calib: Option
               cuboid_side: float, img_h: int, img_w: int, out_f32: Optional[torch.Tensor],
               out_bf16: Optional[torch.Tensor], lay: Optional[VolLayout], extra_zero_planes: int = 0) -> None:
     b, h, w, c = feat_cl.shape
-    _check(load_library().sceneego_unproject_f32(
-        _ptr(feat_cl), _ptr(grid), C.byref(calib) if calib is not None else None, b, h, w, c, int(volume_size),
-        C.c_float(cuboid_side), int(img_h), int(img_w), _ptr(out_f32), _ptr(out_bf16),
-        C.byref(lay) if lay is not None else None, int(extra_zero_planes), _stream()), "unproject")
+    _call("sceneego_unproject_f32", feat_cl, feat_cl, grid, C.byref(calib) if calib is not None else None, b, h, w, c,
+          int(volume_size), C.c_float(cuboid_side), int(img_h), int(img_w), out_f32, out_bf16,
+          C.byref(lay) if lay is not None else None, int(extra_zero_planes))
 
 
 def voxelize_depth(depth: torch.Tensor, ray: torch.Tensor, img_h: int, img_w: int, volume_size: int,
                    cuboid_side: float, occ_f32: Optional[torch.Tensor], occ_bf16: Optional[torch.Tensor],
                    lay: Optional[VolLayout], channel: int = 0) -> None:
     b, h, w = depth.shape
-    _check(load_library().sceneego_voxelize_depth_f64(
-        _ptr(depth), b, h, w, _ptr(ray), int(img_h), int(img_w), int(volume_size), C.c_double(cuboid_side),
-        _ptr(occ_f32), _ptr(occ_bf16), C.byref(lay) if lay is not None else None, int(channel), _stream()),
-        "voxelize_depth")
+    _call("sceneego_voxelize_depth_f64", depth, depth, b, h, w, ray, int(img_h), int(img_w), int(volume_size),
+          C.c_double(cuboid_side), occ_f32, occ_bf16, C.byref(lay) if lay is not None else None, int(channel))
 
 
 def voxelize_depth_raw(depth_raw: torch.Tensor, pre_hw, clamp_max: float, ray: torch.Tensor, img_h: int, img_w: int,
                        volume_size: int, cuboid_side: float, occ_f32: Optional[torch.Tensor],
                        occ_bf16: Optional[torch.Tensor], lay: Optional[VolLayout], channel: int = 0) -> None:
-    """Raw depth maps: the dataset's nearest resize to `pre_hw` and clamp fused into the voxelisation."""
+    """Raw depth maps: the dataset's nearest resize to `pre_hw` and clamp fused into the NETWORK's voxelisation."""
     b, h, w = depth_raw.shape
-    _check(load_library().sceneego_voxelize_depth_raw_f64(
-        _ptr(depth_raw), b, h, w, int(pre_hw[0]), int(pre_hw[1]), C.c_float(clamp_max), _ptr(ray), int(img_h), int(img_w),
-        int(volume_size), C.c_double(cuboid_side), _ptr(occ_f32), _ptr(occ_bf16),
-        C.byref(lay) if lay is not None else None, int(channel), _stream()), "voxelize_depth_raw")
+    _call("sceneego_voxelize_depth_raw_f64", depth_raw, depth_raw, b, h, w, int(pre_hw[0]), int(pre_hw[1]),
+          C.c_float(clamp_max), ray, int(img_h), int(img_w), int(volume_size), C.c_double(cuboid_side), occ_f32,
+          occ_bf16, C.byref(lay) if lay is not None else None, int(channel))
+
+
+def voxelize_depth_dataset(depth_raw: torch.Tensor, pre_hw, clamp_max: float, ray: torch.Tensor, volume_size: int,
+                           cuboid_side: float, occ_f32: torch.Tensor) -> None:
+    """The DATASET's voxelisation (dataset/real_depth_utils.py:29-60): map times ray table pixel for pixel, no squash
+    to H x H and no padded columns; the dataset's resize to `pre_hw` and clamp fused into the load."""
+    b, h, w = depth_raw.shape
+    if tuple(ray.shape) != (int(pre_hw[0]), int(pre_hw[1]), 3):
+        raise SceneEgoError("voxelize_depth_dataset: the ray table must be (pre_h, pre_w, 3)")
+    _call("sceneego_voxelize_depth_dataset_f64", depth_raw, depth_raw, b, h, w, int(pre_hw[0]), int(pre_hw[1]),
+          C.c_float(clamp_max), ray, int(volume_size), C.c_double(cuboid_side), occ_f32)
 
 
 def intersect(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int) -> None:
     """channels [c,2c) = channels [0,c) * occupancy (channel 2c), in place (with_intersection)."""
-    _check(load_library().sceneego_intersect_bf16(_ptr(vol_bf16), C.byref(lay), int(batch), int(channels), _stream()),
-           "intersect")
+    _call("sceneego_intersect_bf16", vol_bf16, vol_bf16, C.byref(lay), int(batch), int(channels))
 
 
 def pose_errors(pred: torch.Tensor, gt: torch.Tensor, scale: bool = True, want_aligned: bool = False):
-    """Per-frame MPJPE and PA-MPJPE (fp64) of pred (B,J,3) f32 against gt (B,J,3) f64; optionally the aligned poses,
-    the ground truth align_skeleton returns and the (c, R, t) transforms."""
+    """Per-frame MPJPE and PA-MPJPE (fp64) of pred (B,J,3) f32 or f64 (dtype kept, like the reference's NumPy)
+    against gt (B,J,3) f64; optionally the aligned poses, the ground truth align_skeleton returns and the
+    (c, R, t) transforms."""
     b, j = pred.shape[0], pred.shape[1]
-    pred = pred.contiguous().float()
+    pred = pred.contiguous()
+    if pred.dtype != torch.float64:
+        pred = pred.float()
     gt = gt.contiguous().double()
     mp = torch.empty(b, dtype=torch.float64, device=pred.device)
     pa = torch.empty(b, dtype=torch.float64, device=pred.device)
     al = torch.empty(b, j, 3, dtype=torch.float64, device=pred.device) if want_aligned else None
     go = torch.empty(b, j, 3, dtype=torch.float64, device=pred.device) if want_aligned else None
     tr = torch.empty(b, 13, dtype=torch.float64, device=pred.device) if want_aligned else None
-    _check(load_library().sceneego_pose_errors_f64(_ptr(pred), _ptr(gt), b, j, int(bool(scale)), _ptr(mp), _ptr(pa),
-                                                   _ptr(al), _ptr(go), _ptr(tr), _stream()), "pose_errors")
+    _call("sceneego_pose_errors_f64", pred, pred, int(pred.dtype == torch.float64), gt, b, j, int(bool(scale)), mp, pa,
+          al, go, tr)
     return mp, pa, al, go, tr
 
 
 def pack_volume(x: torch.Tensor, out_bf16: torch.Tensor, lay: VolLayout, c_offset: int = 0) -> None:
     b, c = x.shape[:2]
-    _check(load_library().sceneego_pack_volume_bf16(_ptr(x), b, c, int(c_offset), _ptr(out_bf16), C.byref(lay),
-                                                    _stream()), "pack_volume")
+    _call("sceneego_pack_volume_bf16", x, x, b, c, int(c_offset), out_bf16, C.byref(lay))
 
 
 def unpack_volume(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int) -> torch.Tensor:
     s = 2 * lay.side if lay.s2d else lay.side
     out = torch.empty(batch, channels, s, s, s, dtype=torch.float32, device=vol_bf16.device)
-    _check(load_library().sceneego_unpack_volume_f32(_ptr(vol_bf16), C.byref(lay), batch, channels, _ptr(out),
-                                                     _stream()), "unpack_volume")
+    _call("sceneego_unpack_volume_f32", vol_bf16, vol_bf16, C.byref(lay), batch, channels, out)
     return out
 
 
 def softargmax3d(logits: torch.Tensor, multiplier: float, softmax: bool, axis: Optional[torch.Tensor],
-                 coords: Optional[torch.Tensor], want_volumes: bool):
+                 coords: Optional[torch.Tensor], want_volumes: bool, out_volumes: Optional[torch.Tensor] = None):
     b, j, v = logits.shape[0], logits.shape[1], logits.shape[2]
     lib = load_library()
     ws = torch.empty(lib.sceneego_softargmax_workspace_bytes(b, j, v) // 4, dtype=torch.float32,
                      device=logits.device)
     kp = torch.empty(b, j, 3, dtype=torch.float32, device=logits.device)
-    vol = torch.empty_like(logits) if want_volumes else None
-    _check(lib.sceneego_softargmax3d_f32(_ptr(logits), b, j, v, C.c_float(multiplier), int(bool(softmax)),
-                                         _ptr(axis), _ptr(coords), _ptr(kp), _ptr(vol), _ptr(ws), _stream()),
-           "softargmax3d")
+    vol = None
+    if want_volumes:
+        vol = out_volumes if out_volumes is not None else torch.empty_like(logits)
+    _call("sceneego_softargmax3d_f32", logits, logits, b, j, v, C.c_float(multiplier), int(bool(softmax)), axis, coords,
+          kp, vol, ws)
     return kp, vol

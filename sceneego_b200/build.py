@@ -4,7 +4,13 @@
 
 The library exposes only the C-ABI of include/sceneego_b200.h; Python binds it
 with ctypes (sceneego_b200/_lib.py).  nvcc cross-compiles without a GPU.
+
+Every source is compiled to its own object (in parallel) and linked; a SHA-256 over the sources, the header and
+the flags is stored next to the library (`libsceneego_b200.so.srchash`), and the library is rebuilt whenever that
+hash differs from the current tree's -- a stale prebuilt `.so` shipped with a snapshot is never silently reused.
 """
+import concurrent.futures
+import hashlib
 import os
 import subprocess
 import sys
@@ -12,32 +18,70 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsceneego_b200.so")
-SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "tail.cu", "march.cu", "eval.cu"]
+HASH_FILE = LIB + ".srchash"
+OBJ_DIR = os.path.join(HERE, "build")
+SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "tail.cu", "march.cu", "eval.cu", "handoff.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    deps.append(os.path.join(HERE, "..", "include", "sceneego_b200.h"))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS + _sources()).encode())
+    return h.hexdigest()
+
+
+def recorded_hash() -> str:
+    try:
+        return open(HASH_FILE).read().strip()
+    except OSError:
+        return ""
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(HERE, "..", "include", "sceneego_b200.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB) or recorded_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    want = source_hash()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, r
+
+    objs, failed = [], False
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for src, obj, r in ex.map(compile_one, _sources()):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
+            failed |= r.returncode != 0
+            objs.append(obj)
+    if failed:
+        raise RuntimeError("nvcc failed building libsceneego_b200.so")
+    r = subprocess.run([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                       capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libsceneego_b200.so")
+        raise RuntimeError("nvcc failed linking libsceneego_b200.so")
+    with open(HASH_FILE, "w") as f:
+        f.write(want + "\n")
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="-q" not in sys.argv))

@@ -9,6 +9,9 @@
 namespace sceneego {
 
 void set_error(const char* fmt, ...);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): the attribute is per device, so a
+// process that drives several GPUs needs it on each of them.  Returns SCENEEGO_OK or SCENEEGO_E_CUDA.
+int ensure_max_dynamic_smem(const void* kernel, int bytes);
 
 #define SE_REQUIRE(cond, ...)                      \
   do {                                             \

@@ -59,13 +59,14 @@ __device__ inline void jacobi_eig3(Mat3 a, double (&w)[3], Mat3& e) {
       }
 }
 
-__global__ void __launch_bounds__(128) pose_errors_kernel(const float* __restrict__ pred, const double* __restrict__ gt, int B, int J,
+template <typename TP>
+__global__ void __launch_bounds__(128) pose_errors_kernel(const TP* __restrict__ pred, const double* __restrict__ gt, int B, int J,
                                                          int scale, double* __restrict__ mpjpe, double* __restrict__ pampjpe,
                                                          double* __restrict__ aligned, double* __restrict__ gt_out,
                                                          double* __restrict__ transform) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const float* P = pred + (size_t)b * J * 3;
+  const TP* P = pred + (size_t)b * J * 3;
   const double* Q = gt + (size_t)b * J * 3;
   const double n = (double)J;
   // calculate_error on the raw poses
@@ -160,12 +161,16 @@ __global__ void __launch_bounds__(128) pose_errors_kernel(const float* __restric
 
 using namespace sceneego;
 
-extern "C" int sceneego_pose_errors_f64(const float* d_pred, const double* d_gt, int batch, int joints, int scale,
-                                        double* d_mpjpe, double* d_pampjpe, double* d_aligned, double* d_gt_out,
-                                        double* d_transform, void* stream) {
+extern "C" int sceneego_pose_errors_f64(const void* d_pred, int pred_is_f64, const double* d_gt, int batch, int joints,
+                                        int scale, double* d_mpjpe, double* d_pampjpe, double* d_aligned,
+                                        double* d_gt_out, double* d_transform, void* stream) {
   SE_REQUIRE(d_pred && d_gt && batch > 0 && joints >= 3, "pose_errors: bad argument");
-  pose_errors_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_pred, d_gt, batch, joints, scale ? 1 : 0, d_mpjpe,
-                                                                             d_pampjpe, d_aligned, d_gt_out, d_transform);
+  if (pred_is_f64)
+    pose_errors_kernel<double><<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        (const double*)d_pred, d_gt, batch, joints, scale ? 1 : 0, d_mpjpe, d_pampjpe, d_aligned, d_gt_out, d_transform);
+  else
+    pose_errors_kernel<float><<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        (const float*)d_pred, d_gt, batch, joints, scale ? 1 : 0, d_mpjpe, d_pampjpe, d_aligned, d_gt_out, d_transform);
   SE_CUDA_LAUNCH_CHECK("pose_errors");
   return SCENEEGO_OK;
 }

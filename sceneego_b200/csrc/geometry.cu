@@ -379,14 +379,16 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
                                                       const double* __restrict__ ray, int img_h, int img_w, int V,
                                                       double side, double inv_side, float* __restrict__ occ_f32,
                                                       __nv_bfloat16* __restrict__ occ_bf16,
-                                                      sceneego_vol_layout_t lay, int channel, int batch, int frames_per_block) {
-  // threads cover the img_h source columns only; the zero-padded columns (np.pad, :198) all land on the
-  // zero-depth voxel, which one thread of the launch sets when there is any padding
+                                                      sceneego_vol_layout_t lay, int channel, int batch, int frames_per_block,
+                                                      int cols) {
+  // threads cover the `cols` source columns only (img_h: the network's squash-and-pad of voxel_net_depth.py:197-198;
+  // img_w: the dataset's pixel-for-pixel product of dataset/real_depth_utils.py:31-33); the zero-padded columns
+  // (np.pad, :198) all land on the zero-depth voxel, which one thread of the launch sets when there is any padding
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y;
-  const int pad = (img_w - img_h) / 2;
+  const int pad = (img_w - cols) / 2;
   const int X = xs + pad;
-  const bool in_src = xs < img_h;
+  const bool in_src = xs < cols;
   const bool in_img = in_src;
   // cv2.resize(INTER_NEAREST), model side then dataset side
   int sy = (int)floor(__dmul_rn((double)Y, nm.ify1));
@@ -637,19 +639,21 @@ extern "C" int sceneego_unproject_f32(const float* d_feat, const float* d_grid, 
 
 static int voxelize_impl(const float* d_depth, int batch, int h, int w, int pre_h, int pre_w, float clamp_max,
                          const double* d_ray, int img_h, int img_w, int V, double side, float* d_occ_f32,
-                         void* d_occ_bf16, const sceneego_vol_layout_t* lay, int channel, void* stream) {
+                         void* d_occ_bf16, const sceneego_vol_layout_t* lay, int channel, void* stream,
+                         bool direct = false) {
   SE_REQUIRE(d_depth && d_ray && (d_occ_f32 || d_occ_bf16), "voxelize: null argument");
   SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && pre_h > 0 && pre_w > 0 && img_w >= img_h, "voxelize: bad shape");
   SE_REQUIRE(!d_occ_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
   SE_REQUIRE(!d_occ_bf16 || !lay->s2d || channel % 8 == 0, "voxelize: s2d occupancy follows whole channel groups");
   // several frames per block so that a pixel's ray is fetched once for all of them (grid.z <= 65535 either way)
   const int fpb = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
-  dim3 grid((img_h + 255) / 256, img_h, (batch + fpb - 1) / fpb);     // source columns only
+  const int cols = direct ? img_w : img_h;                            // source columns only
+  dim3 grid((cols + 255) / 256, img_h, (batch + fpb - 1) / fpb);
   sceneego_vol_layout_t L = lay ? *lay : sceneego_vol_layout_t{};
   NearestMaps nm;
   // OpenCV: inv_scale = (double)dsize / ssize; ifx = 1. / inv_scale
   nm.ify1 = 1.0 / ((double)img_h / (double)pre_h);
-  nm.ifx1 = 1.0 / ((double)img_h / (double)pre_w);
+  nm.ifx1 = 1.0 / ((double)cols / (double)pre_w);
   nm.ify0 = (h == pre_h && w == pre_w) ? 1.0 : 1.0 / ((double)pre_h / (double)h);
   nm.ifx0 = (h == pre_h && w == pre_w) ? 1.0 : 1.0 / ((double)pre_w / (double)w);
   nm.pre_h = pre_h; nm.pre_w = pre_w; nm.clamp_max = clamp_max;
@@ -657,10 +661,10 @@ static int voxelize_impl(const float* d_depth, int batch, int h, int w, int pre_
   const bool pow2 = side > 0 && frexp(side, &e2) == 0.5;       // side == 2^(e2-1): divide == exact multiply
   if (pow2)
     voxelize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 1.0 / side,
-                                                                  d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb);
+                                                                  d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb, cols);
   else
     voxelize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 0.0,
-                                                                   d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb);
+                                                                   d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb, cols);
   SE_CUDA_LAUNCH_CHECK("voxelize");
   return SCENEEGO_OK;
 }
@@ -679,6 +683,14 @@ extern "C" int sceneego_voxelize_depth_raw_f64(const float* d_depth_raw, int bat
                                                const sceneego_vol_layout_t* lay, int channel, void* stream) {
   return voxelize_impl(d_depth_raw, batch, h, w, pre_h, pre_w, clamp_max, d_ray, img_h, img_w, V, side, d_occ_f32,
                        d_occ_bf16, lay, channel, stream);
+}
+
+extern "C" int sceneego_voxelize_depth_dataset_f64(const float* d_depth_raw, int batch, int h, int w, int pre_h, int pre_w,
+                                                   float clamp_max, const double* d_ray, int V, double side,
+                                                   float* d_occ_f32, void* stream) {
+  // dataset/real_depth_utils.py:29-43: the (pre_h, pre_w) map times the (pre_h, pre_w) ray table, pixel for pixel
+  return voxelize_impl(d_depth_raw, batch, h, w, pre_h, pre_w, clamp_max, d_ray, pre_h, pre_w, V, side, d_occ_f32,
+                       nullptr, nullptr, 0, stream, true);
 }
 
 extern "C" int sceneego_intersect_bf16(void* d_vol, const sceneego_vol_layout_t* lay, int batch, int c, void* stream) {

@@ -420,17 +420,7 @@ int launch_conv_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const
   march_fn fn = pick_march(op.cin / 16, p.cin2_planes / 2, op.cout / 16, two);
   SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_march instantiation for cin=%d cin2=%d cout=%d", op_index, op.cin,
              p.src2 ? op.cin2 : 0, op.cout);
-  {
-    static march_fn configured[16];
-    static int n_configured = 0;
-    bool done = false;
-    for (int c = 0; c < n_configured; ++c) done |= (configured[c] == fn);
-    if (!done) {
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-      if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-      if (n_configured < 16) configured[n_configured++] = fn;
-    }
-  }
+  if (int rc = ensure_max_dynamic_smem((const void*)fn, (int)kMaxSmem)) return rc;
   // CTAs take equal contiguous ranges of (item, plane) pairs; at least 16 planes each so that the one or two
   // extra input planes at the ends of a partial march stay a small fraction
   const int slots = kNumSMs * (two ? 2 : 1);

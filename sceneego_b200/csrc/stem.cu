@@ -431,13 +431,8 @@ int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   p.off_bar = p.off_bias + 128;
   p.n_items = (int)((n_pos + STEM_L - 1) / STEM_L);
   const size_t smem_bytes = (size_t)p.off_bar + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_s2d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_s2d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-    configured = true;
-  }
+  if (int rc = ensure_max_dynamic_smem((const void*)stem_s2d_tc_kernel<1>, (int)kMaxSmem)) return rc;
+  if (int rc = ensure_max_dynamic_smem((const void*)stem_s2d_tc_kernel<2>, (int)kMaxSmem)) return rc;
   if (p.cg == 2) {
     const int groups = (p.n_items + 1) / 2;
     cudaLaunchConfig_t cfg;

@@ -363,12 +363,7 @@ int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   SE_REQUIRE((const char*)p.w2 == (const char*)p.w1 + 2048 && (const char*)p.w3 == (const char*)p.w1 + 4096 &&
                  ((uintptr_t)p.w1 & 15) == 0, "v2v_run: op %d: tail weights must be one aligned 5 KB segment", op_index);
   const size_t smem_bytes = 5888 + (size_t)TT_GROUPS * 2 * TT_TILE_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-    configured = true;
-  }
+  if (int rc = ensure_max_dynamic_smem((const void*)tail_tc_kernel, (int)smem_bytes)) return rc;
   const int64_t n_tiles = (p.n_pos + 127) / 128;
   int64_t blocks = (n_tiles + TT_GROUPS - 1) / TT_GROUPS;
   if (blocks > kNumSMs) blocks = kNumSMs;

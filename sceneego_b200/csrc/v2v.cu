@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <mutex>
 
 namespace sceneego {
 
@@ -789,6 +790,23 @@ __global__ void __launch_bounds__(128) deconv2_kernel(const __grid_constant__ Co
 // host side
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+int ensure_max_dynamic_smem(const void* kernel, int bytes) {
+  struct Entry { int dev; const void* fn; int bytes; };
+  static Entry seen[512];
+  static int n_seen = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i].dev == dev && seen[i].fn == kernel && seen[i].bytes >= bytes) return SCENEEGO_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
+  if (n_seen < 512) seen[n_seen++] = Entry{dev, kernel, bytes};
+  return SCENEEGO_OK;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -977,17 +995,7 @@ static int launch_conv_tc(ConvParams& p, int batch, int op_index, cudaStream_t s
   }
   SE_REQUIRE(fn != nullptr, "v2v_run: op %d: no conv_tc instantiation for ksteps=%d tiles=%d xs=%d wrows=%d cta_pair=%d", op_index,
              p.ksteps, p.tiles, p.xs, p.wrows, p.cg);
-  {
-    static conv_tc_fn configured[96];
-    static int n_configured = 0;
-    bool done = false;
-    for (int c = 0; c < n_configured; ++c) done |= (configured[c] == fn);
-    if (!done) {
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-      if (e != cudaSuccess) { set_error("v2v_run: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SCENEEGO_E_CUDA; }
-      if (n_configured < 96) configured[n_configured++] = fn;
-    }
-  }
+  if (int rc = ensure_max_dynamic_smem((const void*)fn, (int)kMaxSmem)) return rc;
   if (p.cg == 2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -340,7 +340,7 @@ class V2VModel(nn.Module):
         self.back_layers = nn.Sequential(Res3DBlock(32, 32), Basic3DBlock(32, 32, 1), Basic3DBlock(32, 32, 1))
         self.output_layer = nn.Conv3d(32, output_channels, kernel_size=1, stride=1, padding=0)
         self._initialize_weights()
-        self._programs: Dict[Tuple[int, int], _Program] = {}
+        self._programs: Dict[int, _Program] = {}
         self._weights_version = None
 
     def _initialize_weights(self):
@@ -352,12 +352,37 @@ class V2VModel(nn.Module):
 
     # -- program construction --------------------------------------------------
     def invalidate(self):
-        """Drop packed weights (call after changing parameters in place)."""
+        """Drop packed weights and buffer pools (also happens by itself when a parameter or BatchNorm buffer
+        changes, see `_current_version`)."""
         self._programs.clear()
+        self._weights_version = None
 
     def _load_from_state_dict(self, *args, **kwargs):
         super()._load_from_state_dict(*args, **kwargs)
-        self._programs.clear()
+        self.invalidate()
+
+    def _current_version(self):
+        """Fingerprint of every tensor the packed blob is derived from: in-place edits bump `_version`,
+        `.to()` / `.half()` / `load_state_dict(assign=True)` change the storage address."""
+        acc, n = 0, 0
+        for t in self._tracked_tensors():
+            acc = (acc * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+            n += 1
+        return acc, n
+
+    def _tracked_tensors(self):
+        for prm in self.parameters():
+            yield prm
+        for name, buf in self.named_buffers():
+            if not name.endswith("num_batches_tracked"):
+                yield buf
+
+    def _refuse_training(self):
+        # BatchNorm is folded from the running statistics: there is no training-mode forward (the reference is
+        # inference-only too: demo.py:32 / test.py:29 call .eval()); batch statistics would silently differ
+        if self.training:
+            raise _lib.SceneEgoError("V2VModel is inference-only (BatchNorm is folded from the running statistics): "
+                                     "call .eval() first")
 
     def _res(self, pg: _Program, blk: Res3DBlock, x: int, level: int) -> int:
         xs = self.c32_xstack if blk.res_branch[0].out_channels == 32 else 1
@@ -444,11 +469,31 @@ class V2VModel(nn.Module):
         return pg
 
     def program(self, side: int, chunk: int, device) -> _Program:
-        key = (side, chunk)
-        pg = self._programs.get(key)
-        if pg is None or pg.device != device:
-            pg = self._build(side, chunk, device)
-            self._programs[key] = pg
+        """The op program for volumes of `side` holding at least `chunk` frames.  ONE program per side is kept: a
+        smaller batch runs on the existing (larger) buffer pool, a larger one (up to max_chunk, rounded up to a
+        power of two) replaces it -- a ragged last DataLoader batch or the pipeline's ramp never builds a second
+        multi-GB pool.  Rebuilt when a weight or BatchNorm buffer changed since it was packed."""
+        device = torch.device(device)
+        if device.type == "cuda":            # (a CPU device only builds the op list / packed blob: host-logic tests)
+            device = _lib._as_device(device)
+        ver = self._current_version()
+        if ver != self._weights_version:
+            self._programs.clear()
+            self._weights_version = ver
+        pg = self._programs.get(side)
+        if pg is None or pg.device != device or pg.chunk < chunk:
+            want = 1
+            while want < chunk:
+                want *= 2
+            want = max(chunk, min(want, self.max_chunk))
+            self._programs.pop(side, None)
+            pg = None
+            if device.type == "cuda":
+                with _lib.on_device(device):
+                    pg = self._build(side, want, device)
+            else:
+                pg = self._build(side, want, device)
+            self._programs[side] = pg
         return pg
 
     # -- execution -------------------------------------------------------------
@@ -456,22 +501,29 @@ class V2VModel(nn.Module):
         """Run the program on the first `batch` frames staged in pg.in_buf; writes
         logits_out (batch, out, V, V, V) f32.  Returns the number of kernels launched."""
         assert batch <= pg.chunk and logits_out.is_contiguous() and logits_out.dtype == torch.float32
+        self._refuse_training()
+        if logits_out.device != pg.device:
+            raise _lib.SceneEgoError(f"v2v_run: logits on {logits_out.device}, program on {pg.device}")
         pg.buf_ptrs[pg.logits_buf] = C.c_void_p(logits_out.data_ptr())
         if impl is not None:
             for op in pg.op_array:
                 op.impl = impl
         lib = _lib.load_library()
-        rc = lib.sceneego_v2v_run(pg.op_array, len(pg.ops), pg.buf_ptrs, C.c_void_p(pg.blob.data_ptr()), int(batch),
-                                  _lib._stream())
+        with _lib.on_device(pg.device):
+            rc = lib.sceneego_v2v_run(pg.op_array, len(pg.ops), pg.buf_ptrs, C.c_void_p(pg.blob.data_ptr()), int(batch),
+                                      _lib._stream(pg.device))
         _lib._check(rc, "v2v_run")
         return lib.sceneego_v2v_last_launch_count()
 
     def profile_chunk(self, pg: _Program, batch: int, logits_out: torch.Tensor):
         """Like run_chunk but returns [(op, milliseconds)] measured with CUDA events per op."""
+        self._refuse_training()
         pg.buf_ptrs[pg.logits_buf] = C.c_void_p(logits_out.data_ptr())
         ms = (C.c_float * len(pg.ops))()
-        rc = _lib.load_library().sceneego_v2v_run_profile(pg.op_array, len(pg.ops), pg.buf_ptrs,
-                                                          C.c_void_p(pg.blob.data_ptr()), int(batch), _lib._stream(), ms)
+        with _lib.on_device(pg.device):
+            rc = _lib.load_library().sceneego_v2v_run_profile(pg.op_array, len(pg.ops), pg.buf_ptrs,
+                                                              C.c_void_p(pg.blob.data_ptr()), int(batch),
+                                                              _lib._stream(pg.device), ms)
         _lib._check(rc, "v2v_run_profile")
         return [(pg.meta[i], float(ms[i])) for i in range(len(pg.ops))]
 

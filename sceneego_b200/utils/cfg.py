@@ -36,3 +36,13 @@ class AttrDict(dict):
 def load_config(path):
     with open(path) as fin:
         return AttrDict(yaml.safe_load(fin))
+
+
+def default_config(batch_size=4, volume_size=64):
+    """The reference's experiments/sceneego/test/sceneego.yaml (shipped as sceneego_b200/data/sceneego.yaml) with
+    `opt.batch_size` and `model.volume_size` set -- what bench.py, smoke() and the tests construct the module from."""
+    from .. import DEFAULT_CONFIG
+    c = load_config(DEFAULT_CONFIG)
+    c.opt.batch_size = batch_size
+    c.model.volume_size = volume_size
+    return c

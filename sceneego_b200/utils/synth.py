@@ -91,3 +91,13 @@ def synthetic_depth_room(batch: int, ray: np.ndarray, seed: int = 7, h: int = 10
         t = np.where(np.isfinite(t), t, clamp)
         out[b] = np.where(circle, np.minimum(t, clamp), 0.0).astype(np.float32)
     return torch.from_numpy(out)
+
+
+def stage_state_shapes(with_intersection: bool = False, num_joints: int = 15):
+    """(key, shape) of every post-backbone state-dict entry of VoxelNetwork_depth (`process_features.*`,
+    `volume_net.*`), derived from the module classes themselves (no GPU, no golden manifest needed)."""
+    from ..network.v2v import V2VModel
+    m = V2VModel(65 if with_intersection else 33, num_joints)
+    shapes = [("process_features.0.weight", (32, 256, 1, 1)), ("process_features.0.bias", (32,))]
+    shapes += [("volume_net." + k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    return shapes

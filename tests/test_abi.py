@@ -20,7 +20,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list out of sync with the header"
-    assert lib.sceneego_abi_version() == 3
+    hdr = open(os.path.join(util.ROOT, "include", "sceneego_b200.h")).read()
+    assert lib.sceneego_abi_version() == int(re.search(r"#define SCENEEGO_ABI_VERSION (\d+)", hdr).group(1)) == 4
 
 
 def test_struct_layouts_match_header():

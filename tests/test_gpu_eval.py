@@ -50,3 +50,20 @@ def test_pose_errors_scale_false_and_large_batch():
     assert mp0 == 0.0 and pa0 <= 1e-12
     with pytest.raises(Exception):
         ce.calculate_error(torch.zeros(2, 15, 3), torch.zeros(2, 15, 3))   # CPU tensors: no fallback
+
+
+def test_pose_errors_keep_float64_predictions():
+    """The reference's NumPy code keeps the caller's dtype: float64 predictions (e.g. poses loaded from a pickle) are
+    used as they are, not rounded to float32 first."""
+    from sceneego_b200.utils import calculate_errors as ce
+    rng = np.random.default_rng(8)
+    gt = rng.normal(0, 0.5, (7, 15, 3))
+    pred = gt + rng.normal(0, 0.05, (7, 15, 3))                          # float64, not representable in float32
+    mp, pa = ce.evaluate_mpjpe(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda())
+    mp_ref, pa_ref = orc.evaluate_mpjpe(pred, gt)
+    assert abs(mp - mp_ref) <= 1e-14 and abs(pa - pa_ref) <= 1e-12
+    mp32, _ = ce.evaluate_mpjpe(torch.from_numpy(pred.astype(np.float32)).cuda(), torch.from_numpy(gt).cuda())
+    assert abs(mp32 - mp_ref) > 1e-12                                     # the float32 rounding is visible at this gate
+    c, R, t = ce.umeyama(torch.from_numpy(pred[0]).cuda(), torch.from_numpy(gt[0]).cuda())
+    c_ref, R_ref, t_ref = orc.umeyama(pred[0], gt[0])
+    assert abs(c - c_ref) <= 1e-10 and np.abs(R.cpu().numpy() - R_ref).max() <= 1e-10

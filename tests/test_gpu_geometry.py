@@ -139,13 +139,49 @@ def test_voxelize_raw_depth_fused_preprocessing(cam, tables64):
         for i in range(2):
             ref = orc.voxelize_depth(orc.preprocess_depth(raw[i]), tables64.ray, 64, 2.0)
             assert np.array_equal(occ[i].cpu().numpy(), ref), (h, w, i)
-    # the voxel_output=True dataset path (dataset/real_depth_utils.py:29-60) shares the kernel
+    # network-semantics batch helper: raw maps -> the grids the NETWORK builds (for scene_volumes=)
     from sceneego_b200.dataset import real_depth_utils as rdu
-    d = orc.preprocess_depth(g["img_001000_raw"])
-    vox = rdu.depth_map_to_voxel(tables64.ray, torch.from_numpy(d), 2.0, 64)          # reference-order NumPy ray table
-    assert np.array_equal(vox.cpu().numpy(), util.unpack_bits(g["img_001000_v64"], 64))
-    vox2 = rdu.depth_maps_to_voxels(ray, torch.from_numpy(g["img_001000_raw"][None]).cuda(), 2.0, 64)
-    assert torch.equal(vox2[0], vox)
+    vox2 = rdu.depth_maps_to_voxels(ray, torch.from_numpy(g["img_001000_raw"][None]).cuda(), 2.0, 64,
+                                    network_semantics=True)
+    assert np.array_equal(vox2[0].cpu().numpy(), util.unpack_bits(g["img_001000_v64"], 64))
+
+
+def test_dataset_depth_map_to_voxel_vs_reference(cam, tables64):
+    """dataset/real_depth_utils.depth_map_to_voxel (the voxel_output=True path of demo_dataset.py:93-94 /
+    test_dataset.py:145-146): ray table x the full 1280-wide map, pixel for pixel -- NOT the network's squash-and-pad.
+    Against occupancy grids produced by the reference's own function (tests/golden/voxel_dataset.npz), V = 64 / 128,
+    bit-exact; plus raw maps with the dataset's resize + clamp fused, NaN / Inf / negative values vs the oracle."""
+    from sceneego_b200.dataset import real_depth_utils as rdu
+    g, gd = util.golden("voxel.npz"), util.golden("voxel_dataset.npz")
+    maps = {n: orc.preprocess_depth(g[f"{n}_raw"]) for n in ("img_001000", "img_001796", "img_002376")}
+    maps["room"] = synth.synthetic_depth_room(1, tables64.ray)[0].numpy()
+    maps["uniform"] = synth.synthetic_depth_uniform(1)[0].numpy()
+    for V in (64, 128):
+        for name, d in maps.items():
+            want = util.unpack_bits(gd[f"{name}_v{V}"], V)
+            vox = rdu.depth_map_to_voxel(tables64.ray, torch.from_numpy(d), 2.0, V)     # reference-order NumPy ray table
+            assert np.array_equal(vox.cpu().numpy(), want), (name, V)
+            assert np.array_equal(orc.voxelize_depth_dataset(d, tables64.ray, V, 2.0), want), (name, V)
+    # the two semantics really differ (ADVICE r1: 7782 vs 8331 occupied voxels on img_001000)
+    assert int(util.unpack_bits(gd["img_001000_v64"], 64).sum()) == 7782
+    assert int(util.unpack_bits(g["img_001000_v64"], 64).sum()) == 8331
+    # raw maps: dataset resize + clamp fused into the same launch, batch of 3
+    raws = np.stack([g[f"{n}_raw"] for n in ("img_001000", "img_001796", "img_002376")])
+    ray = cam.ray_table_device(1280, 1024, "cuda")
+    occ = rdu.depth_maps_to_voxels(ray, torch.from_numpy(raws).cuda(), 2.0, 64)
+    for i, n in enumerate(("img_001000", "img_001796", "img_002376")):
+        assert np.array_equal(occ[i].cpu().numpy(), util.unpack_bits(gd[f"{n}_v64"], 64)), n
+    rng = np.random.default_rng(13)
+    for h, w in ((104, 144), (333, 517), (1024, 1280)):
+        raw = rng.random((2, h, w), dtype=np.float32) * 14 - 1
+        raw[0, ::5, ::3] = np.nan
+        raw[1, ::7, ::2] = np.inf
+        occ = rdu.depth_maps_to_voxels(ray, torch.from_numpy(raw).cuda(), 2.0, 64)
+        for i in range(2):
+            ref = orc.voxelize_depth_dataset(orc.preprocess_depth(raw[i]), tables64.ray, 64, 2.0)
+            assert np.array_equal(occ[i].cpu().numpy(), ref), (h, w, i)
+    with pytest.raises(_lib.SceneEgoError):
+        rdu.depth_maps_to_voxels(ray, torch.zeros(1, 512, 640, device="cuda"), 2.0, 64, preprocess=False)
 
 
 def test_voxelize_odd_source_size_matches_cv2_rule(cam, tables64):

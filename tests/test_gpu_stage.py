@@ -9,6 +9,23 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
+# bf16 bounds of the V2V logits against the reference's fp32 logits (measured values are printed by the tests and
+# recorded in profiles/r02_parity.txt): relative Frobenius error and largest absolute error over the logit range
+LOGIT_REL_FRO = 2.0e-2
+LOGIT_MAX_OVER_RANGE = 2.0e-2
+SOFTMAX_RTOL = 5.0e-2         # softmaxed volume (output #3), was 0.2 in round 1
+S30_GATE_MM = 80.0            # output layer x30 (sharp softmax), tracked; see profiles/r02_bf16_attribution.txt
+
+
+def _logit_errors(logits, gold_sub, gold_range, stride):
+    """GPU logits (B,J,V,V,V) vs the sub-sampled reference logits (B,J,n): (rel-Frobenius, max-abs / range)."""
+    b, j = gold_sub.shape[:2]
+    mine = logits.reshape(b, j, -1)[:, :, ::stride].cpu().numpy().astype(np.float64)
+    ref = gold_sub.astype(np.float64)
+    rel = float(np.linalg.norm(mine - ref) / np.linalg.norm(ref))
+    mx = float(np.abs(mine - ref).max() / float(gold_range[1] - gold_range[0]))
+    return rel, mx
+
 
 @pytest.fixture(scope="module")
 def tables64():
@@ -45,27 +62,104 @@ def test_attributes_like_reference(net, tables64):
 
 @pytest.mark.parametrize("mode,scale,tol_mm", [("default", 1.0, 0.5), ("random_bn", 1.0, 0.5), ("random_bn", 30.0, None)])
 def test_stage_keypoints_vs_reference(net, tables64, mode, scale, tol_mm):
-    """North-star gate: per-joint 3D output within 0.5 mm MPJPE of the reference PyTorch path.
-    The sharpened case (logits x30) is a stress test reported separately."""
+    """North-star gate: per-joint 3D output within 0.5 mm MPJPE of the reference PyTorch path; the V2V logits
+    themselves against the reference's own (forward hook on its `volume_net`, tests/make_golden_r2.py) within the
+    bf16 bound LOGIT_* below; the softmaxed volume within what that logit bound implies.
+    The sharpened case (output layer x30) is the regime a trained checkpoint lives in: tracked with its own gate."""
     _load(net, mode, scale)
     feat = synth.synthetic_features(2)
     depth = torch.cat([synth.synthetic_depth_room(1, tables64.ray), synth.synthetic_depth_uniform(1)])
-    with torch.no_grad():
-        kp, features, volumes, coord = net.lift(feat.cuda(), net.grid_coord_proj_batch, net.coord_volumes,
-                                                depth_map_batch=depth.cuda())
-    g = util.golden("stage_v64.npz")
+    net.keep_logits = True
+    try:
+        with torch.no_grad():
+            kp, features, volumes, coord = net.lift(feat.cuda(), net.grid_coord_proj_batch, net.coord_volumes,
+                                                    depth_map_batch=depth.cuda())
+        logits = net.last_logits
+    finally:
+        net.keep_logits = False
+    g, gl = util.golden("stage_v64.npz"), util.golden("stage_v64_logits.npz")
     tag = f"{mode}_s{int(scale)}"
     err_mm = orc.mpjpe(kp.cpu().numpy(), g[f"kp_{tag}"]) * 1000.0
-    print(f"MPJPE vs reference [{tag}]: {err_mm:.4f} mm")
-    if tol_mm is not None:
-        assert err_mm <= tol_mm
-    else:
-        assert err_mm <= 80.0   # stress case, not graded: bf16 activations under a x30-sharpened softmax
+    rel, mx = _logit_errors(logits, gl[f"logits_{tag}"], gl[f"logit_range_{tag}"], 257)
+    print(f"[{tag}] MPJPE vs reference {err_mm:.4f} mm; logits rel-Frobenius {rel:.3e}, max-abs/range {mx:.3e}")
+    assert err_mm <= (tol_mm if tol_mm is not None else S30_GATE_MM)
+    assert rel <= LOGIT_REL_FRO and mx <= LOGIT_MAX_OVER_RANGE
     assert features.shape == (2, 32, 1024, 1280) and volumes.shape == (2, 15, 64, 64, 64)
     assert coord is net.coord_volumes
     sm = volumes.reshape(2, 15, -1)[:, :, ::257].cpu().numpy()
     if tol_mm is not None:
-        assert np.allclose(sm, g[f"softmax_{tag}"], rtol=0.2, atol=1e-7)
+        # p = exp(l) / Z: a logit error of at most d changes p by at most a factor exp(2 d)
+        d = mx * float(gl[f"logit_range_{tag}"][1] - gl[f"logit_range_{tag}"][0])
+        assert np.allclose(sm, g[f"softmax_{tag}"], rtol=float(np.expm1(2.2 * d)) + 1e-4, atol=1e-9)
+        assert np.allclose(sm, g[f"softmax_{tag}"], rtol=SOFTMAX_RTOL, atol=1e-9)
+
+
+def test_stage_b64_bench_configuration(tables64):
+    """BASELINE configs[1] as bench.py runs it: 64 frames, one 64-frame V2V chunk (2,112 marching items on 296 CTAs),
+    the bench's rank-0 inputs.  Frames 0 / 21 / 42 / 63 against the unmodified reference's outputs for those frames
+    (tests/golden/stage_v64_b64.npz): keypoints, V2V logits, softmaxed volumes, occupancy counts."""
+    from sceneego_b200.network.voxel_net_depth import VoxelNetwork_depth
+    torch.manual_seed(0)
+    big = VoxelNetwork_depth(util.load_config(batch_size=64), device="cuda", v2v_chunk=64).eval()
+    _load(big, "random_bn", 1.0)
+    g = util.golden("stage_v64_b64.npz")
+    frames = [int(f) for f in g["frames"]]
+    feat = synth.synthetic_features(64, seed=1234).cuda()
+    depth = synth.synthetic_depth_room(64, tables64.ray, seed=7).cuda()
+    big.keep_logits = True
+    with torch.no_grad():
+        kp, features, volumes, _ = big.lift(feat, big.grid_coord_proj_batch, big.coord_volumes, depth_map_batch=depth)
+    assert kp.shape == (64, 15, 3) and features.shape == (64, 32, 1024, 1280)
+    err_mm = orc.mpjpe(kp[frames].cpu().numpy(), g["kp"]) * 1000.0
+    lg = big.last_logits[frames]
+    rng_ = np.array([g["logits"].min(), g["logits"].max()])
+    rel, mx = _logit_errors(lg, g["logits"], rng_, 257)
+    print(f"[B=64 chunk 64] MPJPE vs reference {err_mm:.4f} mm; logits rel-Frobenius {rel:.3e}, max-abs/range {mx:.3e}")
+    assert err_mm <= 0.5 and rel <= LOGIT_REL_FRO and mx <= LOGIT_MAX_OVER_RANGE
+    sm = volumes[frames].reshape(4, 15, -1)[:, :, ::257].cpu().numpy()
+    assert np.allclose(sm, g["softmax"], rtol=SOFTMAX_RTOL, atol=1e-9)
+    pg = big.volume_net.program(64, 64, torch.device("cuda", 0))
+    from sceneego_b200 import _lib
+    occ = _lib.unpack_volume(pg.buffers[pg.in_buf], pg.lay_in, 64, 33)[frames, 32]
+    assert [int(o.sum().item()) for o in occ] == [int(c) for c in g["occupied"]]
+    # every frame of the batch equals the same frame run alone (no cross-frame state at the bench's launch shapes)
+    with torch.no_grad():
+        solo = big.lift(feat[21:22], big.grid_coord_proj_batch, big.coord_volumes, depth_map_batch=depth[21:22])[0]
+    assert torch.allclose(solo[0], kp[21], atol=1e-6)
+    del big
+
+
+@pytest.mark.parametrize("mode,scale,tol_mm", [("default", 1.0, 0.5), ("random_bn", 1.0, 0.5), ("random_bn", 30.0, None)])
+def test_stage_v128_vs_reference(mode, scale, tol_mm):
+    """BASELINE configs[3]: 128^3 voxel cube, B=1, whole stage against the UNMODIFIED reference run at that size
+    (tests/golden/stage_v128.npz): keypoints, sub-sampled V2V logits and softmaxed volume."""
+    from sceneego_b200.network.voxel_net_depth import VoxelNetwork_depth
+    torch.manual_seed(0)
+    net128 = VoxelNetwork_depth(util.load_config(batch_size=1, volume_size=128), device="cuda", v2v_chunk=1).eval()
+    _load(net128, mode, scale)
+    t128 = orc.StageTables(util.CALIB, 128, 2.0)
+    feat = synth.synthetic_features(1, seed=77)
+    depth = synth.synthetic_depth_room(1, t128.ray, seed=78)
+    net128.keep_logits = True
+    with torch.no_grad():
+        kp, _, volumes, _ = net128.lift(feat.cuda(), net128.grid_coord_proj_batch, net128.coord_volumes,
+                                        depth_map_batch=depth.cuda())
+    g = util.golden("stage_v128.npz")
+    tag = f"{mode}_s{int(scale)}"
+    err_mm = orc.mpjpe(kp.cpu().numpy(), g[f"kp_{tag}"]) * 1000.0
+    rel, mx = _logit_errors(net128.last_logits, g[f"logits_{tag}"], g[f"logit_range_{tag}"], 2053)
+    print(f"[V=128 {tag}] MPJPE vs reference {err_mm:.4f} mm; logits rel-Frobenius {rel:.3e}, max-abs/range {mx:.3e}")
+    assert err_mm <= (tol_mm if tol_mm is not None else S30_GATE_MM)
+    assert rel <= LOGIT_REL_FRO and mx <= LOGIT_MAX_OVER_RANGE
+    if tol_mm is not None:
+        sm = volumes.reshape(1, 15, -1)[:, :, ::2053].cpu().numpy()
+        assert np.allclose(sm, g[f"softmax_{tag}"], rtol=SOFTMAX_RTOL, atol=1e-10)
+        if scale == 1.0 and f"occupied_{tag}" in g:
+            pg = net128.volume_net.program(128, 1, torch.device("cuda", 0))
+            from sceneego_b200 import _lib
+            occ = _lib.unpack_volume(pg.buffers[pg.in_buf], pg.lay_in, 1, 33)[0, 32]
+            assert int(occ.sum().item()) == int(g[f"occupied_{tag}"])
+    del net128
 
 
 def test_forward_signature_variants(net, tables64):
@@ -102,12 +196,10 @@ def test_cpu_device_is_rejected():
         _lib.softargmax3d(torch.zeros(1, 1, 4, 4, 4), 1.0, True, torch.zeros(3, 4), None, False)
 
 
-def test_ragged_chunks_and_v128_configuration(tables64):
+def test_ragged_chunks(tables64):
     """Batches that do not divide the V2V chunk (5 frames in chunks of 2, 2, 1) give the poses of the same frames
-    run one chunk at a time; and BASELINE.json configs[3] (128^3 cube) runs through the tensor path and agrees with
-    the CUDA-core checker kernels (the oracle needs minutes per frame at that size)."""
+    run one chunk at a time."""
     from sceneego_b200.network.voxel_net_depth import VoxelNetwork_depth
-    from sceneego_b200.network.v2v import V2VModel
     torch.manual_seed(0)
     small = VoxelNetwork_depth(util.load_config(batch_size=2), device="cuda", v2v_chunk=2).eval()
     _load(small, "random_bn", 1.0)
@@ -118,23 +210,6 @@ def test_ragged_chunks_and_v128_configuration(tables64):
         last = small.lift(feat[4:5], small.grid_coord_proj_batch, small.coord_volumes, depth_map_batch=depth[4:5])[0]
     assert all5.shape == (5, 15, 3) and torch.allclose(all5[4], last[0], atol=1e-6)
     del small
-    m = V2VModel(33, 15).eval()
-    sd = synth.synthetic_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=2, mode="random_bn")
-    m.load_state_dict(sd, strict=True)
-    m = m.cuda()
-    x = torch.randn(1, 33, 128, 128, 128, generator=torch.Generator().manual_seed(1)).abs()
-    x[:, 32] = (x[:, 32] > 1.2).float()
-    x = x.cuda()
-    pg = m.program(128, 1, x.device)
-    from sceneego_b200 import _lib
-    _lib.pack_volume(x, pg.buffers[pg.in_buf], pg.lay_in)
-    a = torch.empty(1, 15, 128, 128, 128, device="cuda")
-    b = torch.empty_like(a)
-    m.run_chunk(pg, 1, a, impl=0)
-    m.run_chunk(pg, 1, b, impl=1)
-    torch.cuda.synchronize()
-    assert torch.isfinite(a).all()
-    assert ((a - b).norm() / b.norm()).item() <= 2e-2
 
 
 @pytest.mark.parametrize("mode", ["default", "random_bn"])

@@ -122,3 +122,33 @@ def test_evaluation_math_restated():
     assert orc.evaluate_mpjpe(pred, gt) == (float(g["mpjpe"]), float(g["pampjpe"]))
     a0, g0 = orc.align_skeleton(pred, gt, scale=False)                   # centred, rotation + translation only
     assert np.abs(g0.mean(axis=1)).max() <= 1e-12 and np.abs(a0.mean(axis=1)).max() <= 1e-5
+
+
+@pytest.mark.parametrize("V", [64, 128])
+def test_dataset_voxel_occupancy_bit_exact(tabs, V):
+    """dataset/real_depth_utils.depth_map_to_voxel (voxel_output=True path): the oracle restatement vs grids produced
+    by the reference's own function (tests/make_golden_r2.py)."""
+    g, gd = util.golden("voxel.npz"), util.golden("voxel_dataset.npz")
+    for name in ("img_001000", "img_002376"):
+        d = orc.preprocess_depth(g[f"{name}_raw"])
+        got = orc.voxelize_depth_dataset(d, tabs[64].ray, V, 2.0)
+        assert np.array_equal(got, util.unpack_bits(gd[f"{name}_v{V}"], V))
+        assert not np.array_equal(got, util.unpack_bits(g[f"{name}_v{V}"], V))     # not the network's semantics
+    d = synth.synthetic_depth_room(1, tabs[64].ray)[0].numpy()
+    assert np.array_equal(orc.voxelize_depth_dataset(d, tabs[64].ray, V, 2.0), util.unpack_bits(gd[f"room_v{V}"], V))
+
+
+def test_stage_b64_sample_vs_reference(tabs):
+    """One of the four sampled frames of the bench's 64-frame batch (BASELINE configs[1]) through the oracle vs the
+    reference's keypoints and its own V2V logits (forward hook)."""
+    g = util.golden("stage_v64_b64.npz")
+    f = int(g["frames"][1])
+    sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn")
+    feat = synth.synthetic_features(64, seed=1234)[f:f + 1].contiguous()
+    depth = synth.synthetic_depth_room(64, tabs[64].ray, seed=7)[f:f + 1].contiguous()
+    with torch.no_grad():
+        kp, _, vol, inter = orc.stage_forward(tabs[64], sd, feat, depth_batch=depth, return_intermediates=True)
+    assert orc.mpjpe(kp.numpy(), g["kp"][1:2]) <= 5e-5
+    lg = inter["logits"].reshape(1, 15, -1)[:, :, ::257].numpy()
+    assert np.linalg.norm(lg - g["logits"][1:2]) / np.linalg.norm(g["logits"][1:2]) <= 1e-5
+    assert int(inter["scene"][0].sum()) == int(g["occupied"][1])

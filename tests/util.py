@@ -27,12 +27,8 @@ def stage_shapes():
 
 
 def load_config(batch_size=4, volume_size=64):
-    from sceneego_b200 import DEFAULT_CONFIG
     from sceneego_b200.utils import cfg
-    c = cfg.load_config(DEFAULT_CONFIG)
-    c.opt.batch_size = batch_size
-    c.model.volume_size = volume_size
-    return c
+    return cfg.default_config(batch_size, volume_size)
 
 
 def unpack_bits(packed, V):
