@@ -386,6 +386,39 @@ def stage_forward(tables: StageTables, sd: Dict[str, torch.Tensor], feat256: tor
     return kp, features, vol
 
 
+def stage_forward_device(tables: StageTables, sd: Dict[str, torch.Tensor], feat256: torch.Tensor,
+                         depth_batch: torch.Tensor, device, timings: bool = False):
+    """The reference forward after the backbone with the reference's OWN op sequence on `device`
+    (network/voxel_net_depth.py:237-273 constructed with device='cuda'): nn.Conv2d + nn.Upsample + ConstantPad2d
+    (:58-63), F.grid_sample(align_corners=True) (utils/op.py:209), the per-frame host loop
+    `depth_map.cpu().numpy() -> NumPy voxelisation -> .to(device)` (:251-257), cuDNN Conv3d V2V, softmax + einsum
+    (utils/op.py:88-94).  fp32 throughout.  `sd`, `feat256`, `depth_batch` live on `device`.  Used by
+    `bench.py --impl reference-gpu` (the reference's single-GPU PyTorch stage) and checked against `stage_forward`
+    in tests/test_oracle_golden.py on the CPU."""
+    import time as _time
+    B, V = feat256.shape[0], tables.V
+    up, pad = tables.image_height, (tables.image_width - tables.image_height) // 2
+    x = F.conv2d(feat256, sd["process_features.0.weight"], sd["process_features.0.bias"])
+    x = F.interpolate(x, size=(up, up))                                  # nn.Upsample(size=...) default mode 'nearest'
+    features = F.pad(x, (pad, pad, 0, 0), value=0.0)
+    grid = tables.grid.to(device).unsqueeze(0).expand(B, -1, -1, -1)
+    lifted = F.grid_sample(features, grid, align_corners=True).view(B, features.shape[1], V, V, V)
+    t0 = _time.perf_counter()
+    scene = []
+    for i in range(B):                                                   # voxel_net_depth.py:251-257
+        d = depth_batch[i].cpu().numpy()
+        scene.append(torch.from_numpy(voxelize_depth(d, tables.ray, V, tables.side, tables.image_height, pad)).to(device))
+    scene = torch.stack(scene, dim=0).unsqueeze(1)
+    t_vox = _time.perf_counter() - t0
+    vol_in = torch.cat([lifted, scene], dim=1)
+    logits = v2v_forward(sd, vol_in, prefix="volume_net.")
+    coord = tables.coord_volume.to(device).unsqueeze(0).expand(B, -1, -1, -1, -1)
+    kp, vol = soft_argmax(logits, coord, True)
+    if timings:
+        return kp, features, vol, {"voxel_loop_s": t_vox}
+    return kp, features, vol
+
+
 # ----------------------------------------------------------------------------
 # evaluation math (SURVEY section 8f row 3)
 # ----------------------------------------------------------------------------

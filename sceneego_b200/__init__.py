@@ -11,3 +11,4 @@ import os
 __version__ = "0.1.0"
 PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_CONFIG = os.path.join(PACKAGE_DIR, "data", "sceneego.yaml")
+DEFAULT_CALIBRATION = os.path.join(PACKAGE_DIR, "data", "fisheye.calibration_05_08.json")

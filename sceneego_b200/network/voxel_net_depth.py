@@ -26,8 +26,9 @@ from ..utils.fisheye.FishEyeCalibrated import FishEyeCameraCalibrated
 from . import pose_resnet
 from .v2v import V2VModel
 
+from .. import DEFAULT_CALIBRATION  # noqa: F401  (re-exported)
+
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEFAULT_CALIBRATION = os.path.join(_PKG, "data", "fisheye.calibration_05_08.json")
 
 
 def _resolve_calibration(path):
@@ -157,10 +158,11 @@ class VoxelNetwork_depth(nn.Module):
         n = self.volume_size ** 3
         if g.dim() != 4 or tuple(g.shape[1:]) != (n, 1, 2) or g.shape[0] < 1:
             raise _lib.SceneEgoError(f"grid_coord_proj_batch must have shape (>=B, {n}, 1, 2), got {tuple(g.shape)}")
-        if g.shape[0] < b:
+        expanded = g.shape[0] == 1 or g.stride(0) == 0        # one table for every frame: any batch size is fine
+        if g.shape[0] < b and not expanded:
             raise _lib.SceneEgoError("grid_coord_proj_batch holds fewer rows than the batch (the reference fails "
                                      "in F.grid_sample here, utils/op.py:209)")
-        if g.shape[0] > 1 and g.stride(0) != 0:
+        if not expanded:
             key = (g.data_ptr(), g._version, tuple(g.shape), b)
             if key != self._grid_checked:
                 if not bool((g[:b] == g[:1]).all()):
@@ -176,11 +178,12 @@ class VoxelNetwork_depth(nn.Module):
         if coord_volumes is None:
             return None
         c, v = coord_volumes, self.volume_size
-        if c.dim() != 5 or tuple(c.shape[1:]) != (v, v, v, 3) or c.shape[0] < b:
+        expanded = c.dim() == 5 and (c.shape[0] == 1 or c.stride(0) == 0)
+        if c.dim() != 5 or tuple(c.shape[1:]) != (v, v, v, 3) or (c.shape[0] < b and not expanded):
             raise _lib.SceneEgoError(f"coord_volumes must have shape (>=B, {v}, {v}, {v}, 3), got {tuple(c.shape)}")
         if c.data_ptr() == self.coord_volume.data_ptr() and c.dtype == self.coord_volume.dtype:
             return None
-        if c.shape[0] > 1 and c.stride(0) != 0:
+        if not expanded:
             key = (c.data_ptr(), c._version, tuple(c.shape), b)
             if key != self._coord_checked:
                 if not bool((c[:b] == c[:1]).all()):

@@ -9,6 +9,9 @@ reused by later `run` calls (copy the result out if it must outlive the next cal
 The FIRST batch of a call has nothing to hide its copy behind (604 MB = 11 ms at PCIe speed for 64 frames), so
 it is ramped: copied and lifted as a quarter, a quarter and a half, each part's kernels overlapping the next
 part's copy -- only the first quarter's copy stays exposed.
+With several ranks (`gather_fn`), every batch's LOCAL poses go to the host as they finish and the poses of all
+batches of the call are all-gathered ONCE at the end (frames are independent: there is no per-batch exchange step, and
+a per-batch collective would make every step run at the pace of the slowest GPU).
 """
 from typing import Iterable, List, Tuple
 
@@ -26,6 +29,7 @@ class HostStagePipeline:
         self.gather_fn = gather_fn
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._host_gathered = None
         self._host_out = []          # pinned result buffers, reused across run() calls (cudaHostAlloc is slow)
         self.ramp_min_batch = 32     # ramp the first batch of a call when it has at least this many frames
 
@@ -73,10 +77,11 @@ class HostStagePipeline:
         # pinned result buffers for every batch of this call BEFORE any GPU work is queued: cudaHostAlloc
         # synchronises the device, so allocating them one by one inside the loop drained the pipeline at every
         # new batch index (a 20-batch call after a 2-batch warm-up ran at a third of the speed)
-        kp_shape = (batches[0][0].shape[0], self.net.num_joints, 3) if batches and self.gather_fn is None else None
+        kp_shape = (batches[0][0].shape[0], self.net.num_joints, 3) if batches else None
         while kp_shape is not None and len(self._host_out) < len(batches):
             self._host_out.append(torch.empty(kp_shape, dtype=torch.float32, pin_memory=True))
         ramp = None
+        local_kps = []
         if batches:
             if batches[0][0].shape[0] >= self.ramp_min_batch:
                 ramp = self._stage_ramped(0, *batches[0])
@@ -99,9 +104,9 @@ class HostStagePipeline:
                     main.wait_event(self.ready[slot])
                     kp = self.net.lift(feat, self.net.grid_coord_proj_batch, self.net.coord_volumes,
                                        depth_map_batch=depth)[0]
-            if self.gather_fn is not None:
-                kp = self.gather_fn(kp)
             self.done[slot].record(main)
+            if self.gather_fn is not None:
+                local_kps.append(kp)
             if i >= len(self._host_out) or self._host_out[i].shape != kp.shape:
                 buf = torch.empty(kp.shape, dtype=kp.dtype, pin_memory=True)
                 if i < len(self._host_out):
@@ -112,5 +117,16 @@ class HostStagePipeline:
             host.copy_(kp, non_blocking=True)
             self.d2h_bytes += kp.numel() * 4
             out.append(host)
+        if self.gather_fn is not None and local_kps:
+            # ONE collective per call: (B_local, n_batches, J, 3) -> (B_total, n_batches, J, 3) in frame order
+            if len({tuple(k.shape) for k in local_kps}) != 1:
+                raise ValueError("HostStagePipeline with gather_fn needs equally sized batches")
+            allkp = self.gather_fn(torch.stack(local_kps, dim=1).contiguous())
+            if self._host_gathered is None or self._host_gathered.shape != allkp.shape:
+                self._host_gathered = torch.empty(allkp.shape, dtype=allkp.dtype, pin_memory=True)
+            self._host_gathered.copy_(allkp, non_blocking=True)
+            self.d2h_bytes += allkp.numel() * 4
+            main.synchronize()
+            return [self._host_gathered[:, i] for i in range(len(batches))]
         main.synchronize()
         return out

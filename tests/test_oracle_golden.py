@@ -152,3 +152,16 @@ def test_stage_b64_sample_vs_reference(tabs):
     lg = inter["logits"].reshape(1, 15, -1)[:, :, ::257].numpy()
     assert np.linalg.norm(lg - g["logits"][1:2]) / np.linalg.norm(g["logits"][1:2]) <= 1e-5
     assert int(inter["scene"][0].sum()) == int(g["occupied"][1])
+
+
+def test_stage_forward_device_equals_stage_forward(tabs):
+    """`stage_forward_device` (the reference's own torch op sequence -- F.interpolate, F.grid_sample -- that
+    `bench.py --impl reference-gpu` times on the B200) against the reference's keypoints, here on the CPU."""
+    g = util.golden("stage_v64.npz")
+    sd = synth.synthetic_state_dict(util.stage_shapes(), seed=0, mode="random_bn")
+    feat = synth.synthetic_features(2)[:1]
+    depth = synth.synthetic_depth_room(1, tabs[64].ray)
+    with torch.no_grad():
+        kp, features, vol, tim = orc.stage_forward_device(tabs[64], sd, feat, depth, torch.device("cpu"), timings=True)
+    assert orc.mpjpe(kp.numpy(), g["kp_random_bn_s1"][:1]) <= 5e-5
+    assert features.shape == (1, 32, 1024, 1280) and tim["voxel_loop_s"] > 0
