@@ -11,10 +11,11 @@ pytestmark = pytest.mark.gpu
 
 # bf16 bounds of the V2V logits against the reference's fp32 logits (measured values are printed by the tests and
 # recorded in profiles/r02_parity.txt): relative Frobenius error and largest absolute error over the logit range
-LOGIT_REL_FRO = 2.0e-2
-LOGIT_MAX_OVER_RANGE = 2.0e-2
+LOGIT_REL_FRO = 1.2e-2          # measured 5.9e-3 .. 7.9e-3 over all configurations (V = 64 / 128, B = 2 / 64, x1 / x30)
+LOGIT_MAX_OVER_RANGE = 8.0e-3   # measured 3.3e-3 .. 4.7e-3
 SOFTMAX_RTOL = 5.0e-2         # softmaxed volume (output #3), was 0.2 in round 1
-S30_GATE_MM = 80.0            # output layer x30 (sharp softmax), tracked; see profiles/r02_bf16_attribution.txt
+S30_GATE_MM = 50.0            # output layer x30 (sharp softmax), tracked: measured 33.9 mm (V=64), 27.5 mm (V=128);
+                              # attribution of the bf16 storage error in profiles/r02_bf16_attribution.txt
 
 
 def _logit_errors(logits, gold_sub, gold_range, stride):
