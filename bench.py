@@ -557,7 +557,7 @@ def stage_kernel_timings(net, feat_d, depth_d, B, args, V, hbm_peak, tc_peak):
     ms = timed(lambda: _lib.feature_conv1x1(feat_d[:n], conv.weight, conv.bias))
     rec("feature_conv1x1", ms, 256 * 64 * 64 * 4 + 64 * 64 * 32 * 4, "read (256,64,64) f32 + write (64,64,32) f32")
     ms = timed(lambda: _lib.unproject(feat32, grid, None, V, 2.0, 1024, 1280, None, in_buf, pg.lay_in,
-                                      extra_zero_planes=(pg.in_pad - 32) // 8))
+                                      extra_zero_planes=pg.extra_zero_planes))
     rec("unproject", ms, 64 * 64 * 32 * 4 + N * 32 * 2 + N * 2 + N * 8,
         "read 0.524 MB features + the grid table, write 32 bf16 channels + the cleared occupancy plane")
     d = depth_d[:n]

@@ -107,13 +107,17 @@ typedef struct sceneego_vol_layout {
                             block position (x>>1,y>>1,z>>1); the occupancy channel (the one after the
                             C feature channels) is ONE extra plane whose cell holds the 8 parity
                             values of the 2x2x2 block as its 8 entries                     */
-  int32_t reserved;
+  int32_t zwin;          /* 1: plane 4 (the one after 32 feature channels) is a Z-WINDOW occupancy plane (input of the
+                            marching stem, SCENEEGO_OP_STEM7_MARCH): cell (x,y,z) holds occ[x][y][z-3 .. z+4] as its 8
+                            entries (zero outside the volume), so one 16-byte cell serves the seven dz taps of a row */
 } sceneego_vol_layout_t;
 
 /* Fill a layout for (side, pad, batch); returns plane_stride (positions). */
 int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layout_t* out);
 /* Space-to-depth layout of a volume of side `full_side` (even): S = full_side/2, pad = 2, s2d = 1. */
 int64_t sceneego_vol_layout_make_s2d(int full_side, int batch, sceneego_vol_layout_t* out);
+/* Input layout of the marching stem: plain planar, pad = 3, zwin = 1 (5 planes: 32 features + z-window occupancy). */
+int64_t sceneego_vol_layout_make_zwin(int side, int batch, sceneego_vol_layout_t* out);
 
 /* Bilinear gather of the (virtually) x`scale`-upsampled, zero-padded feature map at the
  * projected voxel centres.  Replaces Upsample+ConstantPad2d (voxel_net_depth.py:60-61)
@@ -197,6 +201,9 @@ enum { SCENEEGO_OP_CONV = 0, SCENEEGO_OP_MAXPOOL2 = 1, SCENEEGO_OP_DECONV2 = 2,
                                       128-voxel tile, hidden activations in shared memory); blob segment at w_offset:
                                       [w1 32x32][w2 32x32][w3 32x16] bf16 (pack_conv layout), then
                                       [b1 32][b2 32][b3 16] f32; dst = (B,cout_real,S,S,S) f32 */,
+       SCENEEGO_OP_STEM7_MARCH = 6, /* Conv3d(33,16,k7)+BN+ReLU as an x-marching banded GEMM (csrc/stem_march.cu): input plane x
+                                      feeds outputs x-3..x+3 in one N = 128 MMA over a ring of 8 tensor-memory slots with
+                                      rotated weight rows; source layout zwin = 1; weights from sceneego_v2v_pack_stem_march */
        SCENEEGO_OP_CONV3_MARCH = 5 /* Conv3d k3 + folded BN (+ residual / ReLU / fused projection shortcut) with
                                       3*cout <= 256 as an x-marching banded GEMM (csrc/march.cu): the three dx taps of
                                       an input plane are one N = 3*cout MMA into a ring of tensor-memory slots, the
@@ -268,6 +275,15 @@ size_t sceneego_v2v_stem_s2d_weight_bytes(void);
 int sceneego_v2v_pack_stem_s2d(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
                                const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
                                double eps, int n_split, uint16_t* h_w_out, float* h_b_out);
+
+/* Same for SCENEEGO_OP_STEM7_MARCH: sceneego_v2v_stem_march_weight_bytes() bytes of bf16,
+ *   [rotation r 8][chunk: (k-step, dy) x 14, then occupancy][tap: dz x 7 | dy pair x 4][k-chunk 2][128 rows][8]:
+ *   row block s of rotation r holds W[dx = 6 - j], j = (s - r) mod 8 (zeros for j = 7); the occupancy taps multiply
+ *   z-window cells (entry e = dz) of two dy rows per MMA: pairs (0,1) (2,3) (4,5) (5,6), the last one's first half zero. */
+size_t sceneego_v2v_stem_march_weight_bytes(void);
+int sceneego_v2v_pack_stem_march(const float* h_weight, const float* h_bias, const float* h_bn_gamma,
+                                 const float* h_bn_beta, const float* h_bn_mean, const float* h_bn_var,
+                                 double eps, uint16_t* h_w_out, float* h_b_out);
 
 /* Execute `n_ops` steps on `batch` frames.  d_blob: packed weights + biases. */
 int sceneego_v2v_run(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_buffers, const void* d_blob,

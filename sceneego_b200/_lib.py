@@ -23,7 +23,8 @@ SYMBOLS = [
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
     "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16", "sceneego_pose_errors_f64",
-    "sceneego_voxelize_depth_dataset_f64",
+    "sceneego_voxelize_depth_dataset_f64", "sceneego_vol_layout_make_zwin", "sceneego_v2v_stem_march_weight_bytes",
+    "sceneego_v2v_pack_stem_march",
 ]
 
 
@@ -35,7 +36,7 @@ class Calib(C.Structure):
 class VolLayout(C.Structure):
     _fields_ = [("side", C.c_int32), ("pad", C.c_int32), ("pitch_y", C.c_int32), ("pitch_x", C.c_int32),
                 ("guard", C.c_int32), ("frame_pitch", C.c_int32), ("plane_stride", C.c_int64),
-                ("s2d", C.c_int32), ("reserved", C.c_int32)]
+                ("s2d", C.c_int32), ("zwin", C.c_int32)]
 
 
 class V2VOp(C.Structure):
@@ -46,7 +47,7 @@ class V2VOp(C.Structure):
                 ("lay_src", VolLayout), ("lay_dst", VolLayout)]
 
 
-OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D, OP_TAIL_MLP, OP_CONV3_MARCH = 0, 1, 2, 3, 4, 5
+OP_CONV, OP_MAXPOOL2, OP_DECONV2, OP_STEM7_S2D, OP_TAIL_MLP, OP_CONV3_MARCH, OP_STEM7_MARCH = 0, 1, 2, 3, 4, 5, 6
 F_RELU, F_RESIDUAL, F_ADD_AFTER, F_OUT_F32 = 1, 2, 4, 8
 
 _lib = None
@@ -70,6 +71,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sceneego_last_error.restype = C.c_char_p
     lib.sceneego_vol_layout_make.restype = C.c_int64
     lib.sceneego_vol_layout_make_s2d.restype = C.c_int64
+    lib.sceneego_vol_layout_make_zwin.restype = C.c_int64
+    lib.sceneego_v2v_stem_march_weight_bytes.restype = C.c_size_t
     lib.sceneego_v2v_stem_s2d_weight_bytes.restype = C.c_size_t
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
     if lib.sceneego_abi_version() != 4:
@@ -170,6 +173,15 @@ def vol_layout_s2d(full_side: int, batch: int) -> VolLayout:
     rc = load_library().sceneego_vol_layout_make_s2d(int(full_side), int(batch), C.byref(lay))
     if rc < 0:
         raise SceneEgoError("vol_layout_make_s2d: bad arguments")
+    return lay
+
+
+def vol_layout_zwin(side: int, batch: int) -> VolLayout:
+    """Input layout of the marching stem: plain planar, pad 3, plane 4 = z-window occupancy (lay.zwin = 1)."""
+    lay = VolLayout()
+    rc = load_library().sceneego_vol_layout_make_zwin(int(side), int(batch), C.byref(lay))
+    if rc < 0:
+        raise SceneEgoError("vol_layout_make_zwin: bad arguments")
     return lay
 
 

@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsceneego_b200.so")
 HASH_FILE = LIB + ".srchash"
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "tail.cu", "march.cu", "eval.cu", "handoff.cu"]
+SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "stem_march.cu", "tail.cu", "march.cu", "eval.cu", "handoff.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

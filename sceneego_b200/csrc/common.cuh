@@ -80,6 +80,8 @@ constexpr int kNumSMs = 148;
 
 int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
                     bool simt, cudaStream_t st);
+int launch_stem_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
+                      bool simt, cudaStream_t st);
 int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
                     bool simt, cudaStream_t st);
 int launch_conv_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,

@@ -374,6 +374,23 @@ struct NearestMaps {
   float clamp_max;     // depth_map[depth_map > clamp_max] = clamp_max (demo_dataset.py:91); +inf = off
 };
 
+// One occupied voxel into the planar bf16 V2V input (three storage forms, include/sceneego_b200.h).
+__device__ __forceinline__ void set_occupied(__nv_bfloat16* __restrict__ occ, const sceneego_vol_layout_t& lay, int b, int x,
+                                             int y, int z, int channel, int V) {
+  const __nv_bfloat16 one = __float2bfloat16(1.0f);
+  if (lay.zwin) {
+    // z-window plane: entry e of cell (x,y,zc) is occ[x][y][zc-3+e] -> this voxel is entry e of the cells zc = z+3-e
+    const int64_t base = ((int64_t)(channel >> 3) * lay.plane_stride + vol_pos(lay, b, x, y, 0)) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int zc = z + 3 - e;
+      if (zc >= 0 && zc < V) occ[base + (int64_t)zc * 8 + e] = one;
+    }
+  } else {
+    occ[vol_scene_elem(lay, b, x, y, z, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = one;
+  }
+}
+
 template <bool kPow2Side>
 __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__ depth, int h, int w, NearestMaps nm,
                                                       const double* __restrict__ ray, int img_h, int img_w, int V,
@@ -455,13 +472,11 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
     if (any_zero && threadIdx.x == 0 && q0_in) {
       const int c = (int)q0;
       if (occ_f32) occ_f32[(((size_t)b * V + c) * V + c) * V] = 1.0f;
-      if (occ_bf16)
-        occ_bf16[vol_scene_elem(lay, b, c, c, 0, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
+      if (occ_bf16) set_occupied(occ_bf16, lay, b, c, c, 0, channel, V);
     }
     if (ix >= 0) {
       if (occ_f32) occ_f32[(((size_t)b * V + ix) * V + iy) * V + iz] = 1.0f;
-      if (occ_bf16)
-        occ_bf16[vol_scene_elem(lay, b, ix, iy, iz, channel >> 3) + (lay.s2d ? 0 : (channel & 7))] = __float2bfloat16(1.0f);
+      if (occ_bf16) set_occupied(occ_bf16, lay, b, ix, iy, iz, channel, V);
     }
   }
 }
@@ -505,6 +520,18 @@ __global__ void pack_volume_kernel(const float* __restrict__ in, int c, int c_of
   for (int ch = 0; ch < c; ++ch) {
     const int oc = ch + c_offset;
     const __nv_bfloat16 v = __float2bfloat16(in[((size_t)b * c + ch) * S * S * S + n]);
+    if (lay.zwin && oc >= 32) {   // z-window occupancy plane: this thread writes its whole cell = occ[x][y][z-3 .. z+4]
+      if (oc == 32) {
+        __align__(16) __nv_bfloat16 cell[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int zz = z - 3 + e;
+          cell[e] = __float2bfloat16((zz >= 0 && zz < S) ? in[((size_t)b * c + ch) * S * S * S + (n - z + zz)] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(out + ((int64_t)4 * lay.plane_stride + vol_pos(lay, b, x, y, z)) * 8) = *reinterpret_cast<const uint4*>(cell);
+      }
+      continue;
+    }
     if (lay.s2d) {   // stem input: 32 feature channels (4 groups) + the occupancy channel (index 32)
       if (oc < 32) out[vol_cell(lay, b, x, y, z, oc >> 3, 4) * 8 + (oc & 7)] = v;
       else if (oc == 32) out[vol_scene_elem(lay, b, x, y, z, 4)] = v;
@@ -523,7 +550,8 @@ __global__ void unpack_volume_kernel(const __nv_bfloat16* __restrict__ in, scene
   const int z = n % S, y = (n / S) % S, x = n / (S * S);
   for (int ch = 0; ch < c; ++ch) {
     int64_t e;
-    if (lay.s2d) e = ch < 32 ? vol_cell(lay, b, x, y, z, ch >> 3, 4) * 8 + (ch & 7) : vol_scene_elem(lay, b, x, y, z, 4);
+    if (lay.zwin && ch >= 32) e = ((int64_t)4 * lay.plane_stride + vol_pos(lay, b, x, y, z)) * 8 + 3;   // entry 3 = the voxel itself
+    else if (lay.s2d) e = ch < 32 ? vol_cell(lay, b, x, y, z, ch >> 3, 4) * 8 + (ch & 7) : vol_scene_elem(lay, b, x, y, z, 4);
     else e = vol_cell(lay, b, x, y, z, ch >> 3, 0) * 8 + (ch & 7);
     out[((size_t)b * c + ch) * S * S * S + n] = __bfloat162float(in[e]);
   }
@@ -540,10 +568,16 @@ extern "C" int64_t sceneego_vol_layout_make_s2d(int full_side, int batch, scenee
   return rc;
 }
 
+extern "C" int64_t sceneego_vol_layout_make_zwin(int side, int batch, sceneego_vol_layout_t* out) {
+  const int64_t rc = sceneego_vol_layout_make(side, 3, batch, out);
+  if (rc > 0) out->zwin = 1;
+  return rc;
+}
+
 extern "C" int64_t sceneego_vol_layout_make(int side, int pad, int batch, sceneego_vol_layout_t* out) {
   if (side <= 0 || pad < 0 || batch <= 0 || !out) return SCENEEGO_E_INVALID;
   sceneego_vol_layout_t L;
-  L.s2d = 0; L.reserved = 0;
+  L.s2d = 0; L.zwin = 0;
   L.side = side;
   L.pad = pad;
   L.pitch_y = side + pad;
@@ -644,7 +678,7 @@ static int voxelize_impl(const float* d_depth, int batch, int h, int w, int pre_
   SE_REQUIRE(d_depth && d_ray && (d_occ_f32 || d_occ_bf16), "voxelize: null argument");
   SE_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && pre_h > 0 && pre_w > 0 && img_w >= img_h, "voxelize: bad shape");
   SE_REQUIRE(!d_occ_bf16 || (lay && (lay->s2d ? 2 * lay->side : lay->side) == V && channel >= 0), "voxelize: bf16 output needs a matching layout");
-  SE_REQUIRE(!d_occ_bf16 || !lay->s2d || channel % 8 == 0, "voxelize: s2d occupancy follows whole channel groups");
+  SE_REQUIRE(!d_occ_bf16 || !(lay->s2d || lay->zwin) || channel % 8 == 0, "voxelize: s2d / z-window occupancy follows whole channel groups");
   // several frames per block so that a pixel's ray is fetched once for all of them (grid.z <= 65535 either way)
   const int fpb = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
   const int cols = direct ? img_w : img_h;                            // source columns only
@@ -706,7 +740,7 @@ extern "C" int sceneego_pack_volume_bf16(const float* d_in, int batch, int c, in
                                          const sceneego_vol_layout_t* lay, void* stream) {
   SE_REQUIRE(d_in && d_out && lay && batch > 0 && batch <= 65535, "pack_volume: bad argument");
   const int S = lay->s2d ? 2 * lay->side : lay->side;
-  SE_REQUIRE(!lay->s2d || c + c_offset <= 33, "pack_volume: an s2d volume holds 32 feature channels + occupancy");
+  SE_REQUIRE(!(lay->s2d || lay->zwin) || c + c_offset <= 33, "pack_volume: an s2d / z-window volume holds 32 feature channels + occupancy");
   const int N = S * S * S;
   pack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>(d_in, c, c_offset,
                                                                                       (__nv_bfloat16*)d_out, *lay);
@@ -718,7 +752,7 @@ extern "C" int sceneego_unpack_volume_f32(const void* d_in, const sceneego_vol_l
                                           float* d_out, void* stream) {
   SE_REQUIRE(d_in && d_out && lay && batch > 0 && batch <= 65535, "unpack_volume: bad argument");
   const int Sfull = lay->s2d ? 2 * lay->side : lay->side;
-  SE_REQUIRE(!lay->s2d || c <= 33, "unpack_volume: an s2d volume holds 32 feature channels + occupancy");
+  SE_REQUIRE(!(lay->s2d || lay->zwin) || c <= 33, "unpack_volume: an s2d / z-window volume holds 32 feature channels + occupancy");
   const int N = Sfull * Sfull * Sfull;
   unpack_volume_kernel<<<dim3((N + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_in,
                                                                                         *lay, c, d_out);

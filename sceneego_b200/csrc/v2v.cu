@@ -1044,10 +1044,11 @@ static int v2v_run_impl(const sceneego_v2v_op_t* ops, int n_ops, void* const* d_
       ++g_launches;
       continue;
     }
-    if (op.type == SCENEEGO_OP_STEM7_S2D || op.type == SCENEEGO_OP_TAIL_MLP) {
+    if (op.type == SCENEEGO_OP_STEM7_S2D || op.type == SCENEEGO_OP_TAIL_MLP || op.type == SCENEEGO_OP_STEM7_MARCH) {
       const bool simt = op.impl == 1 || force_simt;
       const int rc = op.type == SCENEEGO_OP_STEM7_S2D ? launch_stem_s2d(op, d_buffers, d_blob, batch, i, simt, st)
-                                                      : launch_tail_mlp(op, d_buffers, d_blob, batch, i, simt, st);
+                     : op.type == SCENEEGO_OP_STEM7_MARCH ? launch_stem_march(op, d_buffers, d_blob, batch, i, simt, st)
+                                                          : launch_tail_mlp(op, d_buffers, d_blob, batch, i, simt, st);
       if (rc != SCENEEGO_OK) return rc;
       ++g_launches;
       continue;

@@ -90,7 +90,7 @@ def _pad16(c: int) -> int:
 class _Program:
     """Op list + buffer pool + packed weight blob for one (volume_size, chunk) pair."""
 
-    def __init__(self, side: int, chunk: int, in_channels: int, device, allow_s2d: bool = True):
+    def __init__(self, side: int, chunk: int, in_channels: int, device, allow_s2d: bool = True, stem: str = "march"):
         self.side, self.chunk, self.device = side, chunk, device
         self.ops: List[_lib.V2VOp] = []
         self.buffers: List[torch.Tensor] = []
@@ -102,8 +102,15 @@ class _Program:
         self.in_pad = _pad16(in_channels)
         # stem input.  33 channels (32 lifted features + occupancy): space-to-depth storage read by the
         # 2x2x2-stacked stem kernel (csrc/stem.cu); anything else: plain layout, 7^3 stencil needs 3 zero cells
-        self.s2d = in_channels == 33 and allow_s2d
-        self.lay_in = _lib.vol_layout_s2d(side, chunk) if self.s2d else _lib.vol_layout(side, 3, chunk)
+        # "march" (default): plain layout with pad 3 whose fifth plane is the z-window occupancy plane, read by the
+        # x-marching stem (csrc/stem_march.cu); "s2d": the round-1 2x2x2-stacked stem (csrc/stem.cu)
+        special = in_channels == 33 and allow_s2d
+        self.s2d = special and stem == "s2d"
+        self.zwin = special and stem == "march"
+        self.lay_in = (_lib.vol_layout_s2d(side, chunk) if self.s2d else _lib.vol_layout_zwin(side, chunk) if self.zwin
+                       else _lib.vol_layout(side, 3, chunk))
+        # zero planes the unprojection kernel clears behind the 32 feature channels (the occupancy plane(s))
+        self.extra_zero_planes = 1 if self.zwin else (self.in_pad - 32) // 8
         self.lays = [_lib.vol_layout(side >> l, 1, chunk) for l in range(6)]
         self.level_channels = EncoderDecorder.CHANNELS
         self.in_buf = self._new_buffer(-1)
@@ -115,7 +122,7 @@ class _Program:
     def _new_buffer(self, level: int) -> int:
         if level < 0:
             # s2d: 8 parity sub-volumes x 4 channel groups + 1 plane of occupancy blocks
-            t = _lib.alloc_volume(self.lay_in, 33 * 8 if self.s2d else self.in_pad, self.device)
+            t = _lib.alloc_volume(self.lay_in, 33 * 8 if self.s2d else 40 if self.zwin else self.in_pad, self.device)
         else:
             t = _lib.alloc_volume(self.lays[level], self.level_channels[level], self.device)
         self.buffers.append(t)
@@ -261,6 +268,35 @@ class _Program:
         self.flops += fl
         self.meta.append(dict(kind="conv", cin=33, cout=16, k=7, side=op.lay_dst.side, flops=fl))
 
+    def stem_march(self, conv: nn.Conv3d, bn, src: int, dst: int):
+        """7^3 stem as an x-marching banded GEMM from the z-window input (SCENEEGO_OP_STEM7_MARCH)."""
+        lib = _lib.load_library()
+        assert conv.in_channels == 33 and conv.out_channels == 16 and conv.kernel_size[0] == 7
+        w = conv.weight.detach().float().cpu().contiguous().numpy()
+        bias = conv.bias.detach().float().cpu().contiguous().numpy() if conv.bias is not None else None
+        w_out = np.zeros(lib.sceneego_v2v_stem_march_weight_bytes() // 2, dtype=np.uint16)
+        b_out = np.zeros(16, dtype=np.float32)
+
+        def fp(a):
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        g = bn.weight.detach().float().cpu().contiguous().numpy()
+        bt = bn.bias.detach().float().cpu().contiguous().numpy()
+        mu = bn.running_mean.detach().float().cpu().contiguous().numpy()
+        var = bn.running_var.detach().float().cpu().contiguous().numpy()
+        _lib._check(lib.sceneego_v2v_pack_stem_march(fp(w), fp(bias), fp(g), fp(bt), fp(mu), fp(var), C.c_double(float(bn.eps)),
+                                                     fp(w_out), fp(b_out)), "v2v_pack_stem_march")
+        op = _lib.V2VOp()
+        op.type, op.flags = _lib.OP_STEM7_MARCH, _lib.F_RELU
+        op.src2, op.cin2 = -1, 0
+        op.ksize, op.cin, op.cout, op.cout_real = 7, 33, 16, 16
+        op.src, op.dst, op.res, op.impl, op.xstack, op.cta_pair = src, dst, -1, 0, 1, 1
+        op.w_offset, op.b_offset = self._append_blob(w_out), self._append_blob(b_out)
+        op.lay_src, op.lay_dst = self.lay_of(src), self.lay_of(dst)
+        self.ops.append(op)
+        fl = 2 * 33 * 16 * 343 * op.lay_dst.side ** 3
+        self.flops += fl
+        self.meta.append(dict(kind="conv", cin=33, cout=16, k=7, side=op.lay_dst.side, flops=fl))
+
     def tail_mlp(self, blocks, out_conv: nn.Conv3d, src: int, dst: int):
         """Two 1x1 conv+BN+ReLU blocks and the 1x1 output conv as one op (SCENEEGO_OP_TAIL_MLP)."""
         parts_w, parts_b = [], []
@@ -334,6 +370,7 @@ class V2VModel(nn.Module):
         self.fuse_shortcut = True  # 1x1 projection shortcuts accumulate into the second conv of their Res3DBlock
         self.cta_pair = 2        # 1 = every conv on single CTAs
         self.march = True        # 3^3 convs with Cout = 32: x-marching banded GEMM (csrc/march.cu) instead of x-stacking
+        self.stem = "march"      # 33 -> 16 stem: "march" (csrc/stem_march.cu) or "s2d" (csrc/stem.cu, 2x2x2-stacked)
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 16, 7), Res3DBlock(16, 32),
                                           Res3DBlock(32, 32), Res3DBlock(32, 32))
         self.encoder_decoder = EncoderDecorder()
@@ -414,12 +451,14 @@ class V2VModel(nn.Module):
     def _build(self, side: int, chunk: int, device) -> _Program:
         if side % 32 != 0:
             raise _lib.SceneEgoError("V2V needs a volume side divisible by 32 (five 2x poolings)")
-        pg = _Program(side, chunk, self.input_channels, device)
+        pg = _Program(side, chunk, self.input_channels, device, stem=self.stem)
         ed = self.encoder_decoder
         x = pg.acquire(0)
         # 7^3 stem, Cout = 16: the worst tcgen05 shape (N = 16 costs as much as N = 32 per MMA), so four
         # adjacent x-planes of outputs are stacked into N = 64 (tools/mma_rate.cu for the cost model)
-        if pg.s2d:
+        if pg.zwin:
+            pg.stem_march(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x)
+        elif pg.s2d:
             pg.stem_s2d(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, cta_pair=self.cta_pair)
         else:
             pg.conv(self.front_layers[0].block[0], self.front_layers[0].block[1], pg.in_buf, x, relu=True,

@@ -348,7 +348,7 @@ class VoxelNetwork_depth(nn.Module):
         in_buf = pg.buffers[pg.in_buf]
         img_h, img_w = self.heatmap_shape
         _lib.unproject(feat32, grid, self._calib if self.fused_projection else None, v, float(self.cuboid_side),
-                       img_h, img_w, None, in_buf, pg.lay_in, extra_zero_planes=(pg.in_pad - 32) // 8)
+                       img_h, img_w, None, in_buf, pg.lay_in, extra_zero_planes=pg.extra_zero_planes)
         launches = 1
         if self.with_scene is True:
             scene_ch = 64 if self.with_intersection else 32

@@ -70,6 +70,15 @@ def _voxelize(cam, depth, V, side=2.0):
     _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, side, None, buf2, lay2, channel=32)
     assert torch.equal(_lib.unpack_volume(buf2, lay2, d.shape[0], 33)[:, 32], occ), "s2d scene channel differs"
     assert buf2[:32].abs().max().item() == 0.0, "s2d voxelisation touched a feature plane"
+    # the marching stem's input: occupancy as a z-window plane (cell (x,y,z) = occ[x][y][z-3 .. z+4])
+    lay3 = _lib.vol_layout_zwin(V, d.shape[0])
+    buf3 = _lib.alloc_volume(lay3, 40, "cuda")
+    _lib.voxelize_depth(d.contiguous(), ray, 1024, 1280, V, side, None, buf3, lay3, channel=32)
+    assert torch.equal(_lib.unpack_volume(buf3, lay3, d.shape[0], 33)[:, 32], occ), "z-window scene channel differs"
+    assert buf3[:4].abs().max().item() == 0.0, "z-window voxelisation touched a feature plane"
+    ref3 = _lib.alloc_volume(lay3, 40, "cuda")
+    _lib.pack_volume(occ.unsqueeze(1).contiguous(), ref3, lay3, c_offset=32)      # gather form of the same plane
+    assert torch.equal(buf3[4], ref3[4]), "scattered z-window cells differ from the packed ones"
     return occ.cpu().numpy()
 
 
@@ -245,6 +254,14 @@ def test_unproject_vs_reference_golden(cam, tables64):
                        lay2, extra_zero_planes=1)
         s2d = _lib.unpack_volume(buf2, lay2, 2, 33)
         assert torch.equal(s2d[:, :32], planar[:, :32]) and s2d[:, 32].abs().max().item() == 0.0
+        # ... and in the marching stem's z-window layout (one occupancy plane cleared behind the features)
+        lay3 = _lib.vol_layout_zwin(64, 2)
+        buf3 = _lib.alloc_volume(lay3, 40, "cuda")
+        buf3[4].fill_(1.0)
+        _lib.unproject(feat32, grid, cam.calib_struct(1280, 1024) if fused else None, 64, 2.0, 1024, 1280, None, buf3,
+                       lay3, extra_zero_planes=1)
+        zw = _lib.unpack_volume(buf3, lay3, 2, 33)
+        assert torch.equal(zw[:, :32], planar[:, :32]) and zw[:, 32].abs().max().item() == 0.0
 
 
 def test_materialised_features_and_generic_grid_sample(tables64):

@@ -240,6 +240,40 @@ def test_marching_conv_is_deterministic_and_reuses_buffers():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("V,B", [(16, 2), (32, 3), (64, 1), (32, 7), (64, 5)])
+def test_stem_march(V, B):
+    """7^3 stem as an x-marching banded GEMM (csrc/stem_march.cu): N = 128 over a ring of 8 accumulator slots with
+    rotated weight rows, occupancy as a z-window plane.  vs torch fp32 Conv3d + BN + ReLU, vs the CUDA-core checker
+    walking the same blob, pads untouched, deterministic; (32, 7) and (64, 5) give a CTA several items (ring positions
+    carried from one march to the next) and the last group of a frame with tiles beyond the plane."""
+    from sceneego_b200 import _lib
+    conv, bn = _mk_conv(33, 16, 7, seed=5)
+    g = torch.Generator().manual_seed(V + B)
+    x = util.bf16_round(torch.randn(B, 33, V, V, V, generator=g))
+    x[:, 32] = (x[:, 32] > 0.8).float()                       # occupancy channel is {0,1}
+    x = x.cuda()
+    got, dst, lay, src, lay_s = util.run_stem_s2d(x, conv, bn, impl=0, kind="march")
+    assert lay_s.zwin == 1 and lay_s.pad == 3
+    assert torch.equal(_lib.unpack_volume(src, lay_s, B, 33), x)          # z-window pack/unpack round trip
+    # the z-window plane really holds occ[z-3 .. z+4] in every cell
+    cell = src[4].view(-1, 8)[lay_s.guard + 5 * lay_s.pitch_x + 6 * lay_s.pitch_y + 7].float().cpu()
+    want = torch.stack([x[0, 32, 5, 6, 7 - 3 + e] if 0 <= 7 - 3 + e < V else torch.zeros(()) .cuda() for e in range(8)]).cpu()
+    assert torch.equal(cell, want)
+    _close(got, _ref(x, conv, bn, True), f"stem march V{V}")
+    simt, _, _, _, _ = util.run_stem_s2d(x, conv, bn, impl=1, kind="march")
+    assert ((got - simt).abs() <= 0.0079 * simt.abs() + 1e-4).all()      # same blob, other summation order
+    again, _, _, _, _ = util.run_stem_s2d(x, conv, bn, impl=0, kind="march")
+    assert torch.equal(again, got)
+    plane = dst[0].float()
+    mask = torch.ones(lay.plane_stride, dtype=torch.bool, device=dst.device)
+    idx = torch.arange(V, device=dst.device)
+    for b in range(B):
+        pos = (b * lay.frame_pitch + lay.guard + idx[:, None, None] * lay.pitch_x + idx[None, :, None] * lay.pitch_y
+               + idx[None, None, :]).reshape(-1)
+        mask[pos] = False
+    assert plane[mask].abs().max().item() == 0.0, "pad / guard cells were written"
+
+
 @pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("V,B", [(16, 2), (32, 3), (64, 1)])
 def test_stem_s2d(V, B, pair):

@@ -35,10 +35,15 @@ def test_program_structure_and_flops():
     # ten 3^3 convs with 32 output channels march along x (csrc/march.cu), the other 30 stay on conv_tc
     assert kinds.count(_lib.OP_CONV3_MARCH) == 10 and all(op.cout == 32 and op.ksize == 3 for op in pg.ops if op.type == _lib.OP_CONV3_MARCH)
     assert kinds.count(_lib.OP_CONV) == 30 and kinds.count(_lib.OP_TAIL_MLP) == 1 and kinds.count(_lib.OP_MAXPOOL2) == 5 and kinds.count(_lib.OP_DECONV2) == 5
-    assert kinds[0] == _lib.OP_STEM7_S2D
+    assert kinds[0] == _lib.OP_STEM7_MARCH
     assert pg.flops * 8 == m.flops_per_frame(64)
     assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 33 and pg.ops[0].cout == 16
-    assert pg.ops[0].lay_src.s2d == 1 and pg.ops[0].lay_src.side == 16 and pg.ops[0].lay_src.pad == 2
+    assert pg.ops[0].lay_src.zwin == 1 and pg.ops[0].lay_src.s2d == 0 and pg.ops[0].lay_src.side == 32 and pg.ops[0].lay_src.pad == 3
+    assert pg.extra_zero_planes == 1 and pg.buffers[pg.in_buf].shape[0] == 5          # 4 feature planes + z-window occupancy
+    m2 = V2VModel(33, 15)
+    m2.stem = "s2d"                                                                    # the round-1 stem stays selectable
+    pg2 = m2.program(32, 2, torch.device("cpu"))
+    assert pg2.ops[0].type == _lib.OP_STEM7_S2D and pg2.ops[0].lay_src.s2d == 1 and pg2.ops[0].lay_src.side == 16 and pg2.ops[0].lay_src.pad == 2
     pg32 = V2VModel(32, 15).program(32, 1, torch.device("cpu"))          # no occupancy channel: plain x-stacked stem
     assert pg32.ops[0].type == _lib.OP_CONV and pg32.ops[0].cin == 32 and pg32.ops[0].lay_src.pad == 3
     last = pg.ops[-1]
@@ -189,6 +194,78 @@ def test_stem_s2d_packing_reproduces_conv3d():
     assert (out - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()      # bf16 weights (2^-9 relative each)
     # and the blob's non-zero count is exactly the 343 x 33 x 16 taps, each stored once per stacked voxel it serves
     assert int((w_out != 0).sum()) <= 343 * 33 * 16 * 8
+
+
+def test_stem_march_packing_walked_like_the_kernel_reproduces_conv3d():
+    """sceneego_v2v_pack_stem_march (csrc/stem_march.cu): 8 rotations x 15 chunks; walking the blob the way the kernel
+    does -- input plane x adds one N = 128 product into a ring of 8 accumulator slots with the rotation of its ring
+    position, outputs -3..S+2 are drained in order and the out-of-range ones dropped, the occupancy channel read from
+    z-window cells two dy rows per MMA -- equals Conv3d(33,16,7,pad 3) + BN on bf16 inputs."""
+    lib = _lib.load_library()
+    torch.manual_seed(4)
+    conv = nn.Conv3d(33, 16, 7, padding=3)
+    bn = nn.BatchNorm3d(16).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1); bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 2)
+    w_out = np.zeros(lib.sceneego_v2v_stem_march_weight_bytes() // 2, dtype=np.uint16)
+    b_out = np.zeros(16, dtype=np.float32)
+    keep = [a.detach().float().contiguous().numpy() for a in
+            (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+    ptrs = [k.ctypes.data_as(C.c_void_p) for k in keep]
+    assert lib.sceneego_v2v_pack_stem_march(*ptrs, C.c_double(bn.eps), w_out.ctypes.data_as(C.c_void_p),
+                                            b_out.ctypes.data_as(C.c_void_p)) == 0
+    wf = torch.from_numpy((w_out.astype(np.uint32) << 16).view(np.float32).copy()).double()
+    ROT, FEAT, MMA = 417792 // 2, 28672 // 2, 4096 // 2                    # elements
+    assert wf.numel() == 8 * ROT
+    S, P = 6, 3
+    x = torch.randn(33, S, S, S).bfloat16().double()
+    x[32] = (x[32] > 0.3).double()
+    xp = torch.zeros(33, S, S + 2 * P + 1, S + 2 * P + 1, dtype=torch.float64)       # y/z zero pads (+1 for the pair's 2nd row)
+    xp[:, :, P:P + S, P:P + S] = x
+    # z-window occupancy cells: zw[x][y'][z][e] = occ[x][y'][z-3+e]
+    zw = torch.zeros(S, S + 2 * P + 1, S, 8, dtype=torch.float64)
+    for e in range(8):
+        for z in range(S):
+            if 0 <= z - 3 + e < S:
+                zw[:, :, z, e] = xp[32, :, :, P + z - 3 + e]
+    ring = torch.zeros(8, S, S, 16, dtype=torch.float64)                  # slot, y, z, cout
+    out = torch.zeros(16, S, S, S, dtype=torch.float64)
+    G = 70 * 3                                                            # as if this were the CTA's fourth march of a 64^3 run
+    occ_dy = lambda pr, c: (2 * pr if pr < 3 else 5) + c
+
+    def drain(gi, o):
+        if 0 <= o < S:
+            out[:, o] = ring[gi & 7].permute(2, 0, 1)
+        ring[gi & 7] = 0
+
+    for xi in range(S):
+        r = (G + xi) & 7
+        rot = wf[r * ROT:(r + 1) * ROT]
+        acc = torch.zeros(S, S, 128, dtype=torch.float64)
+        for ks in range(2):
+            for dy in range(7):
+                for dz in range(7):
+                    B = rot[(ks * 7 + dy) * FEAT + dz * MMA:(ks * 7 + dy) * FEAT + (dz + 1) * MMA].reshape(2, 128, 8)
+                    A = xp[ks * 16:(ks + 1) * 16, xi, dy:dy + S, dz:dz + S].reshape(2, 8, S, S)
+                    acc += torch.einsum("geyz,gne->yzn", A, B)
+        for pr in range(4):
+            B = rot[14 * FEAT + pr * MMA:14 * FEAT + (pr + 1) * MMA].reshape(2, 128, 8)
+            A = torch.stack([zw[xi, occ_dy(pr, c):occ_dy(pr, c) + S] for c in range(2)])          # (2, y, z, 8)
+            acc += torch.einsum("gyze,gne->yzn", A, B)
+        idle = (r + 7) & 7
+        assert acc[..., idle * 16:(idle + 1) * 16].abs().max().item() == 0.0                       # the block outside the band is zero
+        assert ring[idle].abs().max().item() == 0.0                                                # ... and lands on a cleared slot
+        ring += acc.reshape(S, S, 8, 16).permute(2, 0, 1, 3)
+        drain(G + xi, xi - 3)                                                                      # output xi-3 is complete
+    for k in range(1, 7):
+        drain(G + S - 1 + k, S - 1 + k - 3)
+    assert ring.abs().max().item() == 0.0
+    out += torch.from_numpy(b_out).double()[:, None, None, None]
+    with torch.no_grad():
+        ref = bn.double()(conv.double()(x[None]))[0]
+    assert (out - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()      # bf16 weights (2^-9 relative each)
+    # dense: every tap stored once per rotation, the eighth row block of every MMA is zero
+    assert int((w_out != 0).sum()) <= 8 * 343 * 33 * 16
 
 
 def test_march_packing_walked_like_the_kernel_reproduces_conv3d():

@@ -89,8 +89,10 @@ def run_single_op(x, conv, bn, relu, res=None, impl=0, pad_src=1, deconv=False, 
     return _lib.unpack_volume(dst, lay_d, B, conv.out_channels), dst, lay_d
 
 
-def run_stem_s2d(x, conv, bn, impl=0, cta_pair=1):
-    """Run the 7^3 stem op (SCENEEGO_OP_STEM7_S2D) on x (B,33,V,V,V) f32 cuda; returns (B,16,V,V,V) f32."""
+def run_stem_s2d(x, conv, bn, impl=0, cta_pair=1, kind="s2d"):
+    """Run the 7^3 stem op on x (B,33,V,V,V) f32 cuda; returns (B,16,V,V,V) f32.
+    kind "s2d": SCENEEGO_OP_STEM7_S2D from the space-to-depth input; "march": SCENEEGO_OP_STEM7_MARCH from the
+    z-window input."""
     from sceneego_b200 import _lib
     from sceneego_b200.network.v2v import _Program
     B, V = x.shape[0], x.shape[2]
@@ -98,16 +100,19 @@ def run_stem_s2d(x, conv, bn, impl=0, cta_pair=1):
     pg.side, pg.chunk, pg.device = V, B, x.device
     pg.ops, pg.buffers, pg.buf_level, pg.free, pg.blob_parts, pg.blob_bytes = [], [], [], {}, [], 0
     pg.flops, pg.meta = 0, []
-    lay_s = _lib.vol_layout_s2d(V, B)
+    lay_s = _lib.vol_layout_s2d(V, B) if kind == "s2d" else _lib.vol_layout_zwin(V, B)
     lay_d = _lib.vol_layout(V, 1, B)
-    src = _lib.alloc_volume(lay_s, 33 * 8, x.device)
+    src = _lib.alloc_volume(lay_s, 33 * 8 if kind == "s2d" else 40, x.device)
     dst = _lib.alloc_volume(lay_d, 16, x.device)
     _lib.pack_volume(x.contiguous(), src, lay_s)
     lays = [lay_s, lay_d]
     pg.buffers = [src, dst]
     pg.buf_level = [0, 0]
     pg.lay_of = lambda i: lays[i]
-    pg.stem_s2d(conv, bn, 0, 1, cta_pair=cta_pair)
+    if kind == "s2d":
+        pg.stem_s2d(conv, bn, 0, 1, cta_pair=cta_pair)
+    else:
+        pg.stem_march(conv, bn, 0, 1)
     pg.ops[0].impl = impl
     pg.finalize()
     global LAST_PROGRAM
