@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--global-frames", type=int, default=0, help="fixed total, sharded over the ranks (strong scaling)")
     ap.add_argument("--sweep", default="", help="comma-separated global frame counts: one JSON line each")
+    ap.add_argument("--sweep-frames-cap", type=int, default=2560,
+                    help="sweep lines time min(--steps, max(2, cap / frames per GPU)) steps (the default line always times --steps)")
     ap.add_argument("--volume-size", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel roofline pass")
@@ -289,6 +291,7 @@ def ours_arm(args):
     import contextlib
     import io
     net = None
+    steps_req = args.steps
     for total_req in totals:
         if total_req is not None:
             B = max(1, total_req // world)
@@ -312,6 +315,8 @@ def ours_arm(args):
             full.update(sd)
             net.load_state_dict(full, strict=True)
         net.materialize_features = features
+        if total_req is not None:
+            args.steps = max(2, min(steps_req, args.sweep_frames_cap // B))
         line = run_config(args, net, B, total, world, rank, local, dev, V, strong, features, graph, sampler, numa)
         if rank == 0:
             emit(line, args)
@@ -489,7 +494,7 @@ def roofline_block(kern, tc_burst, tc_sust, peak_src, V, ms_step, B):
     n = v2v["chunk_frames"]
     launch_ms = c32["ms_per_frame"] * n / max(c32["launches"], 1)
     traffic, traffic_src = None, None
-    hit = ncu_traffic("conv_march_kernel", n, V)
+    hit = ncu_traffic("conv_march_kernel<2, 0, 2, 1>", n, V)     # the plain 32 -> 32 instantiation (6 of the 9 launches)
     if hit:
         traffic = hit[0]["dram_bytes_read"] + hit[0]["dram_bytes_write"]
         traffic_src = hit[1]
