@@ -11,14 +11,11 @@
 // sub-bands of the same array at the volume faces).  Consequences:
 //   * every input plane is staged once per item and feeds three outputs (conv_tc x-stacking: 4 planes per 2);
 //   * the whole weight array (27 taps: 55 KB for 32 -> 32) stays RESIDENT in shared memory -- no weight stream;
-//   * accumulators are a RING of tensor-memory slots, one output plane each: output p is complete when plane p+1
-//     has been issued, its slot is committed to the epilogue and recycled one ring revolution later.  A band whose
-//     three slots would straddle the end of the ring does NOT wrap (two MMAs, N = 32 + N = 64, cost 89.5 cycles
-//     instead of 56 on 2 planes of 8: the tensor pipe was 72 % active against a 74.6 % ceiling for that mix of
-//     shapes, profiles/r02_ncu_march_b64.txt): the last two physical slots are MIRRORS of ring slots 0 and 1, the
-//     band simply runs on into them, and the epilogue adds a mirror to its ring slot when it drains outputs 0 / 1
-//     of a revolution.  Every plane is one dense N = 96 MMA sequence; every MMA accumulates -- the epilogue hands a
-//     drained slot (and its mirror) back cleared (tcgen05.st of zeros).
+//   * accumulators are a RING of 512/Cout tensor-memory slots, one output plane each: output p is complete
+//     when plane p+1 has been issued, its slot is committed to the epilogue and recycled 16 planes later.
+//     Where the three slots of a band straddle the end of the ring the MMA is split in two (2 planes per ring
+//     revolution); every MMA accumulates -- the epilogue hands a drained slot back cleared (tcgen05.st of zeros),
+//     so the slot a plane opens needs no overwriting MMA of its own.
 //   warp 0 = producer (cp.async.bulk of one (cin/8)-plane window per input plane, 2..8-stage ring)
 //   warp 1 = TMEM allocator + the one MMA issuer (an N = 96 MMA takes longer than the 41.5-cycle issue floor)
 //   then 4 or 8 epilogue warps: one or two per TMEM lane quarter (two alternate output planes); row decode
@@ -83,8 +80,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
   uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * B_COUNT);
   constexpr int N0 = 16 * NCH;
   const int S = p.ls.side;
-  constexpr int NPHYS = ((int)TMEM_COLS / N0) > MARCH_MAX_SLOTS ? MARCH_MAX_SLOTS : ((int)TMEM_COLS / N0);   // physical slots (== p.n_slots)
-  constexpr int NS = NPHYS - 2;          // accumulator ring; physical slots NS, NS + 1 mirror ring slots 0, 1 (see the header)
+  constexpr int NS = ((int)TMEM_COLS / N0) > MARCH_MAX_SLOTS ? MARCH_MAX_SLOTS : ((int)TMEM_COLS / N0);   // accumulator ring (== p.n_slots)
 
   for (int i = threadIdx.x; i < N0; i += MARCH_THREADS) s_bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
@@ -192,7 +188,8 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
     const uint32_t w_b = ((sbase >> 4) & 0x3FFFu) | b_lbo;
     const uint32_t w2_b = (((sbase + p.w_bytes) >> 4) & 0x3FFFu) | b2_lbo;
     constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);   // D f32, A/B bf16 K-major, M = 128
-    constexpr uint32_t ID1 = idesc0 | ((uint32_t)(N0 >> 3) << 17);
+    constexpr uint32_t ID1 = idesc0 | ((uint32_t)(N0 >> 3) << 17), ID2 = idesc0 | ((uint32_t)(2 * N0 >> 3) << 17),
+                       ID3 = idesc0 | ((uint32_t)(3 * N0 >> 3) << 17);
     const uint32_t pitch_y = (uint32_t)p.ls.pitch_y;
     const uint32_t win0 = ((sbase + p.off_win) >> 4) & 0x3FFFu;                  // stage 0, in 16-B units
     const uint32_t stage16 = p.stage_bytes >> 4;
@@ -236,16 +233,17 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
         const uint32_t stage = win0 + (uint32_t)ws * stage16;
         const uint32_t a0 = stage | a_lbo;
         if (leader) {
-          // consecutive PHYSICAL slots from the ring position of the first block on: a band that starts in the last
-          // two ring slots runs on into the mirror slots instead of wrapping
+          // consecutive ring slots: run A up to the end of the ring, run B from slot 0
           const int nb = j_hi - j_lo + 1;
           const uint32_t sA = SLOT(gj0 + (uint32_t)j_lo);
-          const uint32_t dA = tmem_u + sA * N0;
-          const uint32_t bA = w_b + (uint32_t)(j_lo * N0);
+          const int nA = nb < NS - (int)sA ? nb : NS - (int)sA, nB = nb - nA;
+          const uint32_t dA = tmem_u + sA * N0, dB = tmem_u;
+          const uint32_t bA = w_b + (uint32_t)(j_lo * N0), bB = w_b + (uint32_t)((j_lo + nA) * N0);
           auto IDN = [&](int n) { return ID1 + (uint32_t)(n - 1) * ((uint32_t)(N0 >> 3) << 17); };
           // every MMA accumulates: the epilogue leaves a drained slot cleared (tcgen05.st of zeros), so the slot a
           // plane opens needs no overwriting first MMA of its own (the N = 64 + N = 32 split cost 33 cycles per plane)
-          RUN(a0, bA, dA, IDN(nb), 1u, false);
+          RUN(a0, bA, dA, IDN(nA), 1u, false);
+          if (nB > 0) RUN(a0, bB, dB, IDN(nB), 1u, false);
           if constexpr (KSTEPS2 > 0) {
             // fused 1x1 shortcut: the plane's own output, from the halo-free window of the second source
             if (xi >= x0 && xi < x1) {
@@ -273,6 +271,9 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
     constexpr int HALVES = MARCH_EPI_WARPS / 4;   // warps per lane quarter: they alternate output planes
     const uint32_t half = (uint32_t)(warp - 2) >> 2;
     const bool has_res = (p.flags & (SCENEEGO_F_RESIDUAL | SCENEEGO_F_ADD_AFTER)) != 0;
+    float bs[N0];
+#pragma unroll
+    for (int j = 0; j < N0; ++j) bs[j] = s_bias[j];
     uint32_t G = G_START;
     for (int it = 0; it < my_items; ++it) {
       int b, cell0, x0, x1;
@@ -309,19 +310,6 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
         tc_wait_ld();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tc_st16_zero(taddr + (uint32_t)(16 * c));    // hand the slot back cleared
-        if (slot < 2) {
-          // ring slots 0 / 1: part of this output was accumulated in the mirror slot (bands that ran past the ring end)
-          const uint32_t maddr = taddr + (uint32_t)NS * N0;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t mir[16];
-            tc_ld16(maddr + (uint32_t)(16 * c), mir);
-            tc_wait_ld();
-            tc_st16_zero(maddr + (uint32_t)(16 * c));
-#pragma unroll
-            for (int j = 0; j < 16; ++j) raw[c][j] = __float_as_uint(__uint_as_float(raw[c][j]) + __uint_as_float(mir[j]));
-          }
-        }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -334,7 +322,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
             unpack8(rc[g], rr);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float t = __uint_as_float(raw[g >> 1][(g & 1) * 8 + j]) + s_bias[8 * g + j];     // shared-memory broadcast
+              float t = __uint_as_float(raw[g >> 1][(g & 1) * 8 + j]) + bs[8 * g + j];
               if (p.flags & SCENEEGO_F_RESIDUAL) t += rr[j];
               if (p.flags & SCENEEGO_F_RELU) t = fmaxf(t, 0.f);
               if (p.flags & SCENEEGO_F_ADD_AFTER) t += rr[j];

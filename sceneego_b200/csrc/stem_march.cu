@@ -53,11 +53,12 @@ struct StemMarchParams {
   sceneego_vol_layout_t ls, ld;
   int batch, relu;
   int groups_per_frame, n_items, cells_per_plane;
+  int n_seg, seg_planes;        // small batches: a march is cut into n_seg x-ranges (3 planes of overlap each side)
   int halo, win_cells;
   int p_slots, w_slots;
   uint32_t win_bytes, pair_bytes;
   uint32_t off_w, off_bias, off_bar;
-  FastDiv fd_gpf, fd_py;
+  FastDiv fd_gpf, fd_py, fd_seg;
 };
 
 __host__ __device__ __forceinline__ int smr_occ_dy(int pair, int c) {   // dy rows of the two K chunks of occupancy MMA `pair`
@@ -104,14 +105,21 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
   tc_fence_after();
 
   const int S = p.ls.side;
-  const int OUTS = S + 6;                              // outputs -3 .. S+2 of a march, drained in this order
   const int my_items = ((int)p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto item_of = [&](int it, int& b, int& cell0, int& n_act) {
+  // item = (frame, group of four tiles, x-segment).  A segment stores outputs [x0, x1); it marches over the input
+  // planes [xa, xb] = [x0 - 3, x1 + 2] clipped to the volume and drains the outputs xa - 3 .. xb + 3 in order.
+  auto item_of = [&](int it, int& b, int& cell0, int& n_act, int& x0, int& x1, int& xa, int& xb) {
     const uint32_t item = blockIdx.x + (uint32_t)it * gridDim.x;
-    b = (int)fdiv(item, p.fd_gpf);
-    cell0 = (int)(item - (uint32_t)b * (uint32_t)p.groups_per_frame) * SMR_L;
+    const uint32_t bg = fdiv(item, p.fd_seg);
+    const int seg = (int)(item - bg * (uint32_t)p.n_seg);
+    b = (int)fdiv(bg, p.fd_gpf);
+    cell0 = (int)(bg - (uint32_t)b * (uint32_t)p.groups_per_frame) * SMR_L;
     const int left = p.cells_per_plane - cell0;
     n_act = left >= SMR_L ? SMR_TILES : (left + 127) / 128;
+    x0 = seg * p.seg_planes;
+    x1 = x0 + p.seg_planes < S ? x0 + p.seg_planes : S;
+    xa = x0 - 3 > 0 ? x0 - 3 : 0;
+    xb = x1 + 2 < S - 1 ? x1 + 2 : S - 1;
   };
   const int pitch_y = p.ls.pitch_y;
 
@@ -119,10 +127,12 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
     // ===================== weight producer =====================
     if (lane == 0) {
       int sl = 0, sph = 0;
+      uint32_t G = 0;
       for (int it = 0; it < my_items; ++it) {
-        const uint32_t G = (uint32_t)it * (uint32_t)OUTS;
-        for (int x = 0; x < S; ++x) {
-          const uint8_t* wr = p.w + (size_t)((G + (uint32_t)x) & 7u) * SMR_ROT_BYTES;
+        int b, cell0, n_act, x0, x1, xa, xb;
+        item_of(it, b, cell0, n_act, x0, x1, xa, xb);
+        for (int x = xa; x <= xb; ++x) {
+          const uint8_t* wr = p.w + (size_t)((G + (uint32_t)(x - xa)) & 7u) * SMR_ROT_BYTES;
           for (int c = 0; c <= SMR_FEAT_CHUNKS; ++c) {
             const uint32_t bytes = c < SMR_FEAT_CHUNKS ? SMR_FEAT_CHUNK : SMR_OCC_CHUNK;
             mbar_wait(BAR(B_WEMPTY + sl), sph ^ 1);
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
             if (++sl == p.w_slots) { sl = 0; sph ^= 1; }
           }
         }
+        G += (uint32_t)(xb - xa + 1 + 6);
       }
     }
   } else if (warp == 1) {
@@ -141,10 +152,10 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
     if (lane == 0) {
       int ps = 0, pph = 0;
       for (int it = 0; it < my_items; ++it) {
-        int b, cell0, n_act;
-        item_of(it, b, cell0, n_act);
+        int b, cell0, n_act, x0, x1, xa, xb;
+        item_of(it, b, cell0, n_act, x0, x1, xa, xb);
         const int64_t q0 = (int64_t)b * p.ls.frame_pitch + p.ls.guard + cell0 - p.halo;
-        for (int x = 0; x < S; ++x) {
+        for (int x = xa; x <= xb; ++x) {
           const int64_t qx = q0 + (int64_t)x * p.ls.pitch_x;
           for (int ph = 0; ph < 3; ++ph) {             // planes (0,1), (2,3), (4 = occupancy)
             const int n_planes = ph < 2 ? 2 : 1;
@@ -171,22 +182,23 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
     const uint32_t d_mine = tmem_u + (uint32_t)t * 128u;
     int ps = 0, sl = 0;
     uint32_t pph = 0, sph = 0;
+    uint32_t G = 0;
     for (int it = 0; it < my_items; ++it) {
-      int b_, cell0_, n_act;
-      item_of(it, b_, cell0_, n_act);
+      int b_, cell0_, n_act, x0_, x1_, xa, xb;
+      item_of(it, b_, cell0_, n_act, x0_, x1_, xa, xb);
       // A tile beyond the end of the plane (the last group of a frame) runs the whole barrier protocol -- its commits
       // arrive at once, the epilogue drains zeros -- and skips only the MMA instructions, so every tile keeps the same
-      // ring position G = it * OUTS that the weight producer derives the rotation from.
+      // ring position G (the running count of drained outputs) that the weight producer derives the rotation from.
       const bool active = t < n_act;
-      const uint32_t G = (uint32_t)it * (uint32_t)OUTS;
       if (it > 0) {
         // all eight slots of the previous march have been drained and cleared
         for (uint32_t k = 1; k <= SMR_RING; ++k)
           mbar_wait_warp(BAR(B_ACC_EMPTY + t * SMR_RING + (int)((G - k) & 7u)), ((G - k) >> 3) & 1u);
       }
-      for (int x = 0; x < S; ++x) {
-        if (x > 0)      // the slot this plane's idle block touches (and the next plane opens): output x-4 is gone
-          mbar_wait_warp(BAR(B_ACC_EMPTY + t * SMR_RING + (int)((G + (uint32_t)x - 1u) & 7u)), ((G + (uint32_t)x - 1u) >> 3) & 1u);
+      for (int x = xa; x <= xb; ++x) {
+        const uint32_t gx = G + (uint32_t)(x - xa);       // ring index of the first band block (output x - 3)
+        if (x > xa)     // the slot this plane's idle block touches (and the next plane opens): output x-4 is gone
+          mbar_wait_warp(BAR(B_ACC_EMPTY + t * SMR_RING + (int)((gx - 1u) & 7u)), ((gx - 1u) >> 3) & 1u);
         for (int ks = 0; ks < 2; ++ks) {
           mbar_wait_warp(BAR(B_PFULL + ps), pph);
           const uint32_t a_org = ((sbase + (uint32_t)ps * p.pair_bytes) >> 4) + (uint32_t)p.halo + (uint32_t)t * 128u;
@@ -224,15 +236,16 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
             }
             tc_commit(BAR(B_WEMPTY + sl));
             tc_commit(BAR(B_PEMPTY + ps));
-            tc_commit(BAR(B_ACC_FULL + t * SMR_RING + (int)((G + (uint32_t)x) & 7u)));      // output x-3 is complete
-            if (x == S - 1)
-              for (uint32_t k = 1; k <= 6; ++k)                                               // and so are S-3 .. S+2
-                tc_commit(BAR(B_ACC_FULL + t * SMR_RING + (int)((G + (uint32_t)x + k) & 7u)));
+            tc_commit(BAR(B_ACC_FULL + t * SMR_RING + (int)(gx & 7u)));                      // output x-3 is complete
+            if (x == xb)
+              for (uint32_t k = 1; k <= 6; ++k)                                               // and so are xb-2 .. xb+3
+                tc_commit(BAR(B_ACC_FULL + t * SMR_RING + (int)((gx + k) & 7u)));
           }
           if (++sl == p.w_slots) { sl = 0; sph ^= 1u; }
           if (++ps == p.p_slots) { ps = 0; pph ^= 1u; }
         }
       }
+      G += (uint32_t)(xb - xa + 1 + 6);
     }
     __syncwarp();
   } else {
@@ -242,10 +255,11 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
     float bs[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) bs[j] = s_bias[j];
+    uint32_t G = 0;
     for (int it = 0; it < my_items; ++it) {
-      int b, cell0, n_act;
-      item_of(it, b, cell0, n_act);
-      const uint32_t G = (uint32_t)it * (uint32_t)OUTS;
+      int b, cell0, n_act, x0, x1, xa, xb;
+      item_of(it, b, cell0, n_act, x0, x1, xa, xb);
+      const int OUTS = xb - xa + 1 + 6;
       bool valid[2];
       int64_t dpos0[2];
 #pragma unroll
@@ -258,7 +272,7 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
         dpos0[tt] = (int64_t)b * p.ld.frame_pitch + p.ld.guard + (int64_t)y * p.ld.pitch_y + z;
       }
       for (int oi = 0; oi < OUTS; ++oi) {
-        const int o = oi - 3;
+        const int o = xa - 3 + oi;
         const uint32_t gi = G + (uint32_t)oi;
         const int slot = (int)(gi & 7u);
 #pragma unroll
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + t * SMR_RING + slot));
-          if (valid[tt] && o >= 0 && o < S) {
+          if (valid[tt] && o >= x0 && o < x1) {
             const int64_t dpos = dpos0[tt] + (int64_t)o * p.ld.pitch_x;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -290,6 +304,7 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
           }
         }
       }
+      G += (uint32_t)OUTS;
     }
   }
   tc_fence_before();
@@ -392,7 +407,18 @@ int launch_stem_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const
   SE_REQUIRE(p.win_cells < 16384 && p.ls.guard >= p.halo, "v2v_run: op %d: stem window too large / guard too small (side %d)", op_index, S);
   p.cells_per_plane = (S - 1) * p.ls.pitch_y + S;
   p.groups_per_frame = (p.cells_per_plane + SMR_L - 1) / SMR_L;
-  p.n_items = batch * p.groups_per_frame;
+  // small batches leave most SMs without an item (B = 1: nine groups): cut every march into x-segments, each paying
+  // six extra input planes, until the launch fills the machine once
+  const int base_items = batch * p.groups_per_frame;
+  int n_seg = kNumSMs / base_items;
+  if (n_seg < 1) n_seg = 1;
+  if (n_seg > 16) n_seg = 16;
+  { const char* e = getenv("SCENEEGO_STEM_SEGMENTS"); if (e && atoi(e) >= 1 && atoi(e) <= 32) n_seg = atoi(e); }
+  int seg_planes = (S + n_seg - 1) / n_seg;
+  if (seg_planes < 4) seg_planes = 4 < S ? 4 : S;
+  n_seg = (S + seg_planes - 1) / seg_planes;
+  p.n_seg = n_seg; p.seg_planes = seg_planes;
+  p.n_items = base_items * n_seg;
   SE_REQUIRE((int64_t)batch * p.ls.frame_pitch + 4096 < (1ll << 31), "v2v_run: op %d: batch * frame_pitch too large for one launch", op_index);
   const uint32_t fixed = 64 + 8 * (2 * SMR_MAX_PSLOTS + 2 * SMR_MAX_WSLOTS + 2 * SMR_TILES * SMR_RING) + 64;
   int p_slots = 3, w_slots = 0;
@@ -410,6 +436,7 @@ int launch_stem_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const
   p.off_bar = p.off_bias + 64;
   p.fd_gpf = make_fastdiv((uint32_t)p.groups_per_frame);
   p.fd_py = make_fastdiv((uint32_t)p.ls.pitch_y);
+  p.fd_seg = make_fastdiv((uint32_t)p.n_seg);
   const size_t smem_bytes = (size_t)p.off_bar + 8 * (2 * SMR_MAX_PSLOTS + 2 * SMR_MAX_WSLOTS + 2 * SMR_TILES * SMR_RING) + 64;
   SE_REQUIRE(smem_bytes <= kMaxSmem, "v2v_run: op %d: stem shared memory plan exceeds 227 KB", op_index);
   if (int rc = ensure_max_dynamic_smem((const void*)stem_march_tc_kernel, (int)kMaxSmem)) return rc;
