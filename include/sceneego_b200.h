@@ -310,6 +310,27 @@ int sceneego_softargmax3d_f32(const float* d_logits, int batch, int joints, int 
                               float multiplier, int softmax, const float* d_axis, const float* d_coords,
                               float* d_keypoints, float* d_volumes_out, void* d_workspace, void* stream);
 
+/* ---- backbone hand-off ------------------------------ */
+
+/* The LAST stage of pose_resnet's deconvolution head -- ConvTranspose2d(256,256,k4,s2,p1,bias=False) + BatchNorm2d + ReLU
+ * (network/pose_resnet.py:203-226,238-240: deconv_layers[6..8]) -- fused with process_features[0] = Conv2d(256,32,1)
+ * (network/voxel_net_depth.py:58-63) in one tcgen05 kernel (bf16 operands, fp32 accumulation): the reference's
+ * (B,256,64,64) f32 `features` map is never written, the stage receives its channel-last input directly.
+ *   sceneego_handoff_pack: host-side fold + repack.  h_deconv_w (256,256,4,4) f32 (ConvTranspose2d layout cin,cout,ky,kx),
+ *       BatchNorm gamma/beta/mean/var (256), h_conv_w (32,256) f32, h_conv_b (32) or NULL ->
+ *       sceneego_handoff_weight_bytes() bytes: [parity 4][tap 4][K-step 16][k-chunk 2][256 rows][8] bf16 (BN scale folded in),
+ *       then the 1x1 weights [K-step 16][k-chunk 2][32 rows][8]; h_b_out = 256 BN shifts + 32 conv biases (f32)
+ *   sceneego_backbone_handoff_f32: d_x (B,256,h,w) f32 NCHW = the output of deconv_layers[0..5] -> d_out (B,2h,2w,32) f32
+ *       channel-last (what sceneego_feature_conv1x1_f32 produces from the 256-channel map); d_workspace of
+ *       sceneego_handoff_workspace_bytes(B,h,w) bytes holds the zero-bordered planar bf16 copy of the input */
+size_t sceneego_handoff_weight_bytes(void);
+size_t sceneego_handoff_workspace_bytes(int batch, int h, int w);
+int sceneego_handoff_pack(const float* h_deconv_w, const float* h_bn_gamma, const float* h_bn_beta, const float* h_bn_mean,
+                          const float* h_bn_var, double eps, const float* h_conv_w, const float* h_conv_b,
+                          uint16_t* h_w_out, float* h_b_out);
+int sceneego_backbone_handoff_f32(const float* d_x, int batch, int cin, int h, int w, const void* d_weights,
+                                  const float* d_bias, void* d_workspace, float* d_out, void* stream);
+
 /* ---- evaluation ------------------------------------ */
 
 /* The metric loop of test.py (dataset/test_dataset.py:102-112) for a batch of poses: replaces calculate_error

@@ -24,7 +24,8 @@ SYMBOLS = [
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
     "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16", "sceneego_pose_errors_f64",
     "sceneego_voxelize_depth_dataset_f64", "sceneego_vol_layout_make_zwin", "sceneego_v2v_stem_march_weight_bytes",
-    "sceneego_v2v_pack_stem_march",
+    "sceneego_v2v_pack_stem_march", "sceneego_handoff_weight_bytes", "sceneego_handoff_workspace_bytes", "sceneego_handoff_pack",
+    "sceneego_backbone_handoff_f32",
 ]
 
 
@@ -73,6 +74,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sceneego_vol_layout_make_s2d.restype = C.c_int64
     lib.sceneego_vol_layout_make_zwin.restype = C.c_int64
     lib.sceneego_v2v_stem_march_weight_bytes.restype = C.c_size_t
+    lib.sceneego_handoff_weight_bytes.restype = C.c_size_t
+    lib.sceneego_handoff_workspace_bytes.restype = C.c_size_t
     lib.sceneego_v2v_stem_s2d_weight_bytes.restype = C.c_size_t
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
     if lib.sceneego_abi_version() != 4:
@@ -342,3 +345,37 @@ def softargmax3d(logits: torch.Tensor, multiplier: float, softmax: bool, axis: O
     _call("sceneego_softargmax3d_f32", logits, logits, b, j, v, C.c_float(multiplier), int(bool(softmax)), axis, coords,
           kp, vol, ws)
     return kp, vol
+
+
+# ---- backbone hand-off -------------------------------------------------------------
+def handoff_pack(deconv_w: torch.Tensor, bn_gamma, bn_beta, bn_mean, bn_var, eps: float, conv_w: torch.Tensor,
+                 conv_b: torch.Tensor, device):
+    """Fold + repack the last ConvTranspose2d(256,256,4,2,1) + BatchNorm2d of pose_resnet's head and the 1x1
+    process_features conv for `backbone_handoff`; returns (weights uint8 device tensor, bias f32 device tensor)."""
+    import numpy as np
+    lib = load_library()
+    if tuple(deconv_w.shape) != (256, 256, 4, 4) or tuple(conv_w.shape[:2]) != (32, 256):
+        raise SceneEgoError("handoff_pack: expects ConvTranspose2d(256,256,4) and Conv2d(256,32,1) weights")
+    arrs = [t.detach().float().cpu().contiguous().numpy() for t in
+            (deconv_w, bn_gamma, bn_beta, bn_mean, bn_var, conv_w.reshape(32, 256), conv_b)]
+    w_out = np.zeros(lib.sceneego_handoff_weight_bytes() // 2, dtype=np.uint16)
+    b_out = np.zeros(256 + 32, dtype=np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib.sceneego_handoff_pack(ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]), ptr(arrs[4]), C.c_double(eps),
+                                     ptr(arrs[5]), ptr(arrs[6]), ptr(w_out), ptr(b_out)), "handoff_pack")
+    return torch.from_numpy(w_out.view(np.uint8)).to(device), torch.from_numpy(b_out).to(device)
+
+
+def backbone_handoff(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (B,256,h,w) f32 NCHW = the input of pose_resnet's last deconvolution stage -> (B,2h,2w,32) f32 channel-last,
+    the stage's `feat32` (deconv + BN + ReLU + 1x1 conv fused on tcgen05; the 256-channel map is never written)."""
+    b, c, h, w = x.shape
+    x = x.contiguous().float()
+    if out is None:
+        out = torch.empty(b, 2 * h, 2 * w, 32, dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (b, 2 * h, 2 * w, 32) or out.dtype != torch.float32:
+        raise SceneEgoError("backbone_handoff: bad output buffer")
+    ws = torch.empty(load_library().sceneego_handoff_workspace_bytes(b, h, w), dtype=torch.uint8, device=x.device)
+    _call("sceneego_backbone_handoff_f32", x, x, b, c, h, w, weights, bias, ws, out)
+    return out

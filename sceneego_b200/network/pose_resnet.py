@@ -64,6 +64,13 @@ class PoseResNet(nn.Module):
         layers += [Bottleneck(self.inplanes, planes) for _ in range(1, n)]
         return nn.Sequential(*layers)
 
+    def forward_before_last_deconv(self, x):
+        """Everything up to the input of the last deconvolution stage: (B,256,32,32).  The hand-off kernel
+        (csrc/handoff.cu) fuses that stage with the volumetric stage's 1x1 conv."""
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.deconv_layers[:6](x)
+
     def forward(self, x):
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))

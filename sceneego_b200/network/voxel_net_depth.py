@@ -42,7 +42,8 @@ def _resolve_calibration(path):
 
 class VoxelNetwork_depth(nn.Module):
     def __init__(self, config, device='cuda', materialize_features=True, materialize_volumes=True,
-                 fused_projection=False, v2v_chunk=32, persistent_features=False, graph_max_batch=0):
+                 fused_projection=False, v2v_chunk=32, persistent_features=False, graph_max_batch=0,
+                 backbone_handoff=False):
         """Extra keyword switches (all default to reference-identical outputs):
         materialize_features / materialize_volumes: build outputs #2 / #3 of the reference
             forward (168 MB and 15.7 MB per frame, ignored by demo.py:57 / test.py:54);
@@ -52,7 +53,10 @@ class VoxelNetwork_depth(nn.Module):
         persistent_features: output #2 is a view of ONE buffer that the next call overwrites (default: a fresh
             tensor per call, like the reference).
         graph_max_batch: batches of at most this many frames replay a captured CUDA graph of the whole lift
-            (demo.py runs batch 1: ~70 launches of a few microseconds each are launch-bound otherwise); 0 = off."""
+            (demo.py runs batch 1: ~70 launches of a few microseconds each are launch-bound otherwise); 0 = off.
+        backbone_handoff: forward() fuses the backbone's last deconvolution stage (ConvTranspose2d + BN + ReLU) with
+            process_features[0] in one tensor-core kernel (bf16 operands, fp32 accumulation) instead of running the
+            stage in torch and the 1x1 conv in fp32; `lift()` is unaffected."""
         super().__init__()
         dev = torch.device(device)
         if dev.type != 'cuda':
@@ -61,6 +65,8 @@ class VoxelNetwork_depth(nn.Module):
         dev = _lib._as_device(dev)
         self.device = device
         self.persistent_features = persistent_features
+        self.backbone_handoff = bool(backbone_handoff)
+        self._handoff_cache = None
         self.graph_max_batch = int(graph_max_batch)
         self._graphs = {} if graph_max_batch > 0 else None
         self.num_joints = config.model.backbone.num_joints
@@ -203,16 +209,24 @@ class VoxelNetwork_depth(nn.Module):
         feat = backbone_features.contiguous().float()
         if not feat.is_cuda:
             raise _lib.SceneEgoError("sceneego_b200 ops need CUDA tensors (no CPU fallback)")
-        dev = feat.device
-        b = feat.shape[0]
+        conv = self.process_features[0]
+        return self._lift_feat32(lambda out: _lib.feature_conv1x1(feat, conv.weight, conv.bias, out=out),
+                                 feat.shape[0], (feat.shape[2], feat.shape[3]), feat.device, 1,
+                                 grid_coord_proj_batch, coord_volumes, scene_volumes, depth_map_batch)
+
+    def _lift_feat32(self, make_feat32, b, hw, dev, feat_launches, grid_coord_proj_batch, coord_volumes, scene_volumes,
+                     depth_map_batch):
+        """The stage from `feat32` on.  `make_feat32(out)` produces the (B,h,w,32) channel-last f32 map of
+        process_features[0] -- from the backbone's 256-channel features (lift) or fused with the backbone's last
+        deconvolution (forward with backbone_handoff=True) -- into `out` (None: a fresh tensor)."""
         v = self.volume_size
         if b <= self.graph_max_batch and self._graphs is not None:
-            out = self._lift_graphed(feat, grid_coord_proj_batch, coord_volumes, scene_volumes, depth_map_batch)
+            out = self._lift_graphed(make_feat32, b, hw, dev, feat_launches, grid_coord_proj_batch, coord_volumes,
+                                     scene_volumes, depth_map_batch)
             if out is not NotImplemented:
                 return out
-        conv = self.process_features[0]
-        feat32 = _lib.feature_conv1x1(feat, conv.weight, conv.bias)           # (B,64,64,32) channel-last
-        launches = 1
+        feat32 = make_feat32(None)                                            # (B,64,64,32) channel-last
+        launches = feat_launches
         features = None
         feat_done = None
         main = torch.cuda.current_stream(dev)
@@ -268,14 +282,15 @@ class VoxelNetwork_depth(nn.Module):
         self.last_logits = logits if self.keep_logits else None
         return kp, features, volumes, self.coord_volumes
 
-    def _lift_graphed(self, feat, grid_coord_proj_batch, coord_volumes, scene_volumes, depth_map_batch):
+    def _lift_graphed(self, make_feat32, b, hw, dev, feat_launches, grid_coord_proj_batch, coord_volumes, scene_volumes,
+                      depth_map_batch):
         """Small batches (demo.py runs batch 1): the ~68 launches from the gather to the V2V logits replay as ONE
         captured CUDA graph over static buffers; the 1x1 feature conv (live weights), the copy of the scene input
         into its static buffer, the soft-argmax and outputs #2 / #3 (fresh tensors) stay outside the graph.
         Returns NotImplemented when the eager path must handle the call."""
         if self.with_scene is True and scene_volumes is None and depth_map_batch is None:
             return NotImplemented
-        dev, b, v = feat.device, feat.shape[0], self.volume_size
+        v = self.volume_size
         vn = self.volume_net
         if min(vn.max_chunk, self.graph_max_batch) < b:
             return NotImplemented
@@ -293,12 +308,11 @@ class VoxelNetwork_depth(nn.Module):
                0 if grid is None else grid.data_ptr(), self.depth_preprocess, id(pg), dev.index)
         g = self._graphs.get(key)
         main = torch.cuda.current_stream(dev)
-        conv = self.process_features[0]
         if g is None:
             if len(self._graphs) >= 8 or any(e["pg"] is not pg for e in self._graphs.values()):
                 self._graphs.clear()                        # a rebuilt program (new weights) invalidates every capture
             g = {"pg": pg, "grid": grid,
-                 "feat32": torch.empty(b, feat.shape[2], feat.shape[3], 32, dtype=torch.float32, device=dev),
+                 "feat32": torch.empty(b, hw[0], hw[1], 32, dtype=torch.float32, device=dev),
                  "src": None if src is None else torch.empty(src.shape, dtype=torch.float32, device=dev),
                  "logits": torch.empty(b, self.num_joints, v, v, v, dtype=torch.float32, device=dev)}
 
@@ -306,7 +320,7 @@ class VoxelNetwork_depth(nn.Module):
                 n = self._fill_v2v_input(pg, g["feat32"], grid, g["src"] if kind == "scene" else None,
                                          g["src"] if kind == "depth" else None)
                 return n + vn.run_chunk(pg, b, g["logits"])
-            _lib.feature_conv1x1(feat, conv.weight, conv.bias, out=g["feat32"])
+            make_feat32(g["feat32"])
             if src is not None:
                 g["src"].copy_(src)
             body()                                          # eager warm-up: per-device kernel attributes get set
@@ -316,7 +330,7 @@ class VoxelNetwork_depth(nn.Module):
                 g["launches"] = body()
             g["graph"] = graph
             self._graphs[key] = g
-        _lib.feature_conv1x1(feat, conv.weight, conv.bias, out=g["feat32"])
+        make_feat32(g["feat32"])
         if src is not None:
             g["src"].copy_(src)
         features, feat_done = None, None
@@ -336,7 +350,7 @@ class VoxelNetwork_depth(nn.Module):
                                         self._axis if coords is None else None, coords, self.materialize_volumes)
         if feat_done is not None:
             main.wait_event(feat_done)
-        self.last_launches = 1 + g["launches"] + (3 if self.materialize_volumes else 2) + (1 if features is not None else 0)
+        self.last_launches = feat_launches + g["launches"] + (3 if self.materialize_volumes else 2) + (1 if features is not None else 0)
         self.last_logits = g["logits"].clone() if self.keep_logits else None
         return kp, features, volumes, self.coord_volumes
 
@@ -377,8 +391,31 @@ class VoxelNetwork_depth(nn.Module):
         return launches
 
     def forward(self, images, grid_coord_proj_batch, coord_volumes, scene_volumes=None, depth_map_batch=None):
+        if self.backbone_handoff:
+            # the backbone stops before its last deconvolution stage; that stage, its
+            # BatchNorm + ReLU and process_features[0] run as ONE tcgen05 kernel that emits the stage's channel-last
+            # feat32 directly (the heatmap head `final_layer`, unused by the reference forward, is skipped)
+            if self.training:
+                raise _lib.SceneEgoError("VoxelNetwork_depth is inference-only: call .eval() first")
+            x2 = self.backbone.forward_before_last_deconv(images).contiguous().float()
+            w, bias = self._handoff_weights(x2.device)
+            return self._lift_feat32(lambda out: _lib.backbone_handoff(x2, w, bias, out=out), x2.shape[0],
+                                     (2 * x2.shape[2], 2 * x2.shape[3]), x2.device, 2, grid_coord_proj_batch,
+                                     coord_volumes, scene_volumes, depth_map_batch)
         heatmaps, features = self.backbone(images)
         return self.lift(features, grid_coord_proj_batch, coord_volumes, scene_volumes, depth_map_batch)
+
+    def _handoff_weights(self, device):
+        """Packed weights of the hand-off kernel, rebuilt when one of their sources changed (in-place edits bump
+        `_version`, .to()/load_state_dict(assign=True) change the storage)."""
+        dc, bn, pf = self.backbone.deconv_layers[6], self.backbone.deconv_layers[7], self.process_features[0]
+        src = (dc.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, pf.weight, pf.bias)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (str(device),)
+        if self._handoff_cache is None or self._handoff_cache[0] != key:
+            w, bias = _lib.handoff_pack(dc.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps),
+                                        pf.weight, pf.bias, device)
+            self._handoff_cache = (key, w, bias)
+        return self._handoff_cache[1], self._handoff_cache[2]
 
     # kept for API parity with the reference (network/voxel_net_depth.py:194-205): one frame
     def depth_map_to_voxel_numpy(self, depth):

@@ -1,7 +1,7 @@
 """Round-2 golden vectors, again produced by running the UNMODIFIED reference on CPU.
 
 Run in the build container only (needs /root/reference):
-    OPENCV_IO_ENABLE_OPENEXR=1 python tests/make_golden_r2.py [--b64-only|--v128-only|--v64-only|--dataset-only]
+    OPENCV_IO_ENABLE_OPENEXR=1 python tests/make_golden_r2.py [--b64-only|--v128-only|--v64-only|--dataset-only|--forward-only]
 
 Adds to tests/golden/:
   stage_v64_logits.npz   the reference's OWN V2V logits (forward hook on `volume_net`) for the three B=2 stage
@@ -11,6 +11,7 @@ Adds to tests/golden/:
                          cross-frame state)
   stage_v128.npz         BASELINE configs[3]: V=128, B=1, whole stage (keypoints, sub-sampled logits and softmax)
   voxel_dataset.npz      dataset/real_depth_utils.depth_map_to_voxel (the `voxel_output=True` path), V=64 / 128
+  forward_v64.npz        the whole reference forward from `images` (backbone included), B = 2
 While generating, the oracle restatement is asserted against the reference in full.
 """
 import json
@@ -140,6 +141,38 @@ def make_v128(config, Net, calib_path):
     _report_update(**rep)
 
 
+def make_forward_golden(config, Net, calib_path):
+    """The WHOLE reference forward, backbone included (network/voxel_net_depth.py:224-275 from `images`): seeded
+    synthetic weights for all 699 state-dict entries, B = 2 images.  Golden for forward() with and without the
+    backbone hand-off."""
+    net, _ = _net(config, Net, 64, 2)
+    tabs = orc.StageTables(calib_path, 64, 2.0)
+    shapes = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    sd = synth.synthetic_state_dict(shapes, seed=0, mode="random_bn")
+    net.load_state_dict(sd, strict=True)
+    img = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(3))
+    depth = synth.synthetic_depth_room(2, tabs.ray, seed=4)
+    grabbed = []
+    h = net.volume_net.register_forward_hook(lambda m, i, o: grabbed.append(o.detach()))
+    with torch.no_grad():
+        kp, feats, vol, _ = net(img, net.grid_coord_proj_batch, net.coord_volumes, depth_map_batch=depth)
+        _, bb_feat = net.backbone(img)
+    h.remove()
+    logits = grabbed[0]
+    # the oracle's post-backbone restatement from the reference backbone's features agrees
+    with torch.no_grad():
+        kp_o, _, _ = orc.stage_forward(tabs, {k: v for k, v in sd.items() if not k.startswith("backbone.")}, bb_feat,
+                                       depth_batch=depth)
+    e = orc.mpjpe(kp_o.numpy(), kp.numpy())
+    assert e <= 5e-5, f"forward golden: oracle stage differs from the reference forward: {e}"
+    np.savez_compressed(os.path.join(OUT, "forward_v64.npz"), kp=kp.numpy(),
+                        logits=logits.reshape(2, 15, -1)[:, :, ::LOGIT_STRIDE_V64].numpy(),
+                        logit_range=np.array([logits.min().item(), logits.max().item(), logits.std().item()]),
+                        backbone_features=bb_feat[:, ::16, ::4, ::4].numpy(),
+                        backbone_features_absmax=np.array(bb_feat.abs().max().item()))
+    _report_update(forward_v64_mpjpe_oracle_stage_vs_ref_m=e)
+
+
 def make_dataset_voxel(calib_path):
     """dataset/real_depth_utils.py:29-60 imported unmodified; its last line `voxel_torch[idx.T] = 1` is evaluated with
     the torch-1.13.1 tuple rule like the network's by patching ONLY that function."""
@@ -197,6 +230,8 @@ def main():
         make_b64(config, Net, calib_path)
     if not only or "--v128-only" in only:
         make_v128(config, Net, calib_path)
+    if not only or "--forward-only" in only:
+        make_forward_golden(config, Net, calib_path)
     os.chdir(cwd)
     print(open(os.path.join(OUT, "report.json")).read())
 
