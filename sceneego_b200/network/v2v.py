@@ -157,7 +157,7 @@ class _Program:
         return self._append_blob(w_out), self._append_blob(b_out)
 
     def pack_arrays(self, conv: nn.Module, bn: Optional[nn.BatchNorm3d], cin_pad: int, cout_pad: int,
-                    xstack: int = 1, n_split: int = 1, march: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+                    xstack: int = 1, n_split: int = 1, march=False) -> Tuple[np.ndarray, np.ndarray]:
         transposed = isinstance(conv, nn.ConvTranspose3d)
         w = conv.weight.detach().float().cpu().contiguous().numpy()
         k = w.shape[-1]
@@ -194,7 +194,7 @@ class _Program:
 
     # -- ops -----------------------------------------------------------------
     def conv(self, conv: nn.Conv3d, bn, src: int, dst: int, relu: bool, res: int = -1, out_f32: bool = False,
-             xstack: int = 1, cta_pair: int = 1, shortcut=None, march: bool = False):
+             xstack: int = 1, cta_pair: int = 1, shortcut=None, march=False):
         """shortcut = (conv1x1, bn, src2): the projection shortcut of a Res3DBlock (v2v.py:32-43) accumulated into
         the same GEMM tile instead of being written out and re-read as a residual.
         march: run as SCENEEGO_OP_CONV3_MARCH (x-marching banded GEMM, csrc/march.cu); xstack / cta_pair unused."""
@@ -203,7 +203,7 @@ class _Program:
         if march:
             assert k == 3 and not out_f32 and cout_pad == conv.out_channels
             xstack = cta_pair = 1
-            w_main, b_main = self.pack_arrays(conv, bn, cin_pad, cout_pad, march=True)
+            w_main, b_main = self.pack_arrays(conv, bn, cin_pad, cout_pad, march=march)
             if shortcut is None:
                 w_off, b_off = self._append_blob(w_main), self._append_blob(b_main)
             else:
@@ -626,6 +626,7 @@ class V2VModelSimple(V2VModel):
         self.input_channels, self.output_channels = input_channels, output_channels
         self.max_chunk = max_chunk
         self.c32_xstack, self.fuse_shortcut, self.cta_pair, self.march = 2, True, 2, True
+        self.stem = "march"
         self.front_layers = nn.Sequential(Basic3DBlock(input_channels, 32, 7))
         self.encoder_decoder = EncoderDecoderSimple()
         self.back_layers = nn.Sequential(Basic3DBlock(32, 32, 1))
