@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--raw-depth", action="store_true",
                     help="e2e ships raw 512x640 depth maps; the dataset's resize + clamp run inside the voxelisation")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--act-dtype", default="bf16", choices=["bf16", "f16"],
+                    help="storage type of V2V activations / weights (bf16 = BASELINE configs[1]; f16 = the fp16 build)")
     ap.add_argument("--profile-ops", default="", help="write the per-op V2V timing table to this file")
     ap.add_argument("--out", default="", help="also append the JSON line(s) to this file")
     return ap.parse_args()
@@ -441,7 +443,7 @@ def run_config(args, net, B, total, world, rank, local, dev, V, strong, features
     ms_step = ms_total / args.steps
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": args.act_dtype, "data": "synthetic",
             "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes // args.steps,
                     "d2h_bytes_per_step": pipe.d2h_bytes // args.steps,
@@ -636,6 +638,7 @@ def stage_kernel_timings(net, feat_d, depth_d, B, args, V, hbm_peak, tc_peak):
 
 if __name__ == "__main__":
     a = parse()
+    os.environ["SCENEEGO_ACT_DTYPE"] = a.act_dtype          # read by sceneego_b200._lib when the library is first loaded
     if a.impl == "reference":
         reference_arm(a)
     elif a.impl == "reference-gpu":

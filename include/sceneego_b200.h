@@ -38,6 +38,10 @@ enum {
 };
 
 int sceneego_abi_version(void);
+/* Storage type of the V2V activations and packed weights this library was compiled for: 0 = bf16
+ * (libsceneego_b200.so, the default), 1 = IEEE fp16 with saturating stores (libsceneego_b200_f16.so, built from the
+ * same sources with -DSCENEEGO_ACT_F16).  The "bf16" in entry-point names means "the 16-bit activation type". */
+int sceneego_act_dtype(void);
 const char* sceneego_last_error(void);
 
 /* Scaramuzza omnidirectional camera (utils/fisheye/FishEyeCalibrated.py:8-16,

@@ -13,10 +13,33 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsceneego_b200.so")
+# Storage type of V2V activations / packed weights: "bf16" (default; BASELINE configs[1]) or "f16" (the same sources
+# compiled with -DSCENEEGO_ACT_F16: 3 more mantissa bits, saturating stores).  One per process, chosen by the
+# environment variable SCENEEGO_ACT_DTYPE or set_act_dtype() before the library is first loaded.
+_ACT = os.environ.get("SCENEEGO_ACT_DTYPE", "bf16").lower()
+LIB_PATHS = {"bf16": os.path.join(_HERE, "libsceneego_b200.so"), "f16": os.path.join(_HERE, "libsceneego_b200_f16.so")}
+LIB_PATH = LIB_PATHS["bf16"]
+
+
+def set_act_dtype(name: str) -> None:
+    global _ACT
+    name = {"fp16": "f16", "float16": "f16", "bfloat16": "bf16"}.get(name.lower(), name.lower())
+    if name not in LIB_PATHS:
+        raise SceneEgoError(f"unknown activation dtype {name!r} (bf16 or f16)")
+    if _lib is not None and name != _ACT:
+        raise SceneEgoError("the activation dtype is fixed once the library is loaded (one per process)")
+    _ACT = name
+
+
+def act_dtype_name() -> str:
+    return _ACT
+
+
+def act_torch_dtype():
+    return torch.float16 if _ACT == "f16" else torch.bfloat16
 
 SYMBOLS = [
-    "sceneego_abi_version", "sceneego_last_error", "sceneego_ray_table_f64", "sceneego_project_voxels_f32",
+    "sceneego_abi_version", "sceneego_act_dtype", "sceneego_last_error", "sceneego_ray_table_f64", "sceneego_project_voxels_f32",
     "sceneego_feature_conv1x1_f32", "sceneego_features_upsample_pad_f32", "sceneego_vol_layout_make",
     "sceneego_unproject_f32", "sceneego_voxelize_depth_f64", "sceneego_pack_volume_bf16",
     "sceneego_unpack_volume_f32", "sceneego_v2v_pack_conv", "sceneego_v2v_run", "sceneego_v2v_run_profile",
@@ -63,7 +86,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or LIB_PATHS[_ACT]
     if not os.path.exists(p):
         raise SceneEgoError(
             f"{p} not found: build it with `python -m sceneego_b200.build` "
@@ -80,6 +103,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
     if lib.sceneego_abi_version() != 4:
         raise SceneEgoError("libsceneego_b200.so ABI version mismatch")
+    if path is None and lib.sceneego_act_dtype() != (1 if _ACT == "f16" else 0):
+        raise SceneEgoError(f"{p} was not compiled for {_ACT} activations")
     if path is None:
         _lib = lib
     return lib
@@ -189,9 +214,9 @@ def vol_layout_zwin(side: int, batch: int) -> VolLayout:
 
 
 def alloc_volume(lay: VolLayout, channels: int, device) -> torch.Tensor:
-    """Zero-initialised planar padded bf16 volume: (C/8, plane_stride, 8)."""
+    """Zero-initialised planar padded volume of the 16-bit activation type: (C/8, plane_stride, 8)."""
     assert channels % 8 == 0
-    return torch.zeros(channels // 8, lay.plane_stride, 8, dtype=torch.bfloat16, device=device)
+    return torch.zeros(channels // 8, lay.plane_stride, 8, dtype=act_torch_dtype(), device=device)
 
 
 # ---- thin per-op wrappers (argument checking lives in C) ---------------------

@@ -17,7 +17,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libsceneego_b200.so")
+LIB = os.path.join(HERE, "libsceneego_b200.so")            # bf16 activations / weights (default)
+LIB_F16 = os.path.join(HERE, "libsceneego_b200_f16.so")    # the same sources with -DSCENEEGO_ACT_F16 (fp16 storage)
 HASH_FILE = LIB + ".srchash"
 OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "stem_march.cu", "tail.cu", "march.cu", "eval.cu", "handoff.cu"]
@@ -48,36 +49,45 @@ def recorded_hash() -> str:
 
 
 def _stale() -> bool:
-    return not os.path.exists(LIB) or recorded_hash() != source_hash()
+    return not (os.path.exists(LIB) and os.path.exists(LIB_F16)) or recorded_hash() != source_hash()
+
+
+VARIANTS = [("bf16", LIB, []), ("f16", LIB_F16, ["-DSCENEEGO_ACT_F16"])]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Build both libraries (bf16 and fp16 activation storage) from the same sources; returns the default one."""
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)
     want = source_hash()
 
-    def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
-        return src, obj, r
+    def compile_one(job):
+        tag, src, extra = job
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", f".{tag}.o"))
+        r = subprocess.run([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return tag, src, obj, r
 
-    objs, failed = [], False
+    jobs = [(tag, src, extra) for tag, _, extra in VARIANTS for src in _sources()]
+    jobs.sort(key=lambda j: -os.path.getsize(os.path.join(CSRC, j[1])))          # the long compiles first
+    objs = {tag: [] for tag, _, _ in VARIANTS}
+    failed = False
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        for src, obj, r in ex.map(compile_one, _sources()):
+        for tag, src, obj, r in ex.map(compile_one, jobs):
             if verbose or r.returncode != 0:
-                sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
+                sys.stderr.write(f"---- {src} [{tag}]\n{r.stdout}{r.stderr}")
             failed |= r.returncode != 0
-            objs.append(obj)
+            objs[tag].append(obj)
     if failed:
-        raise RuntimeError("nvcc failed building libsceneego_b200.so")
-    r = subprocess.run([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
-                       capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed linking libsceneego_b200.so")
+        raise RuntimeError("nvcc failed building libsceneego_b200")
+    for tag, lib, _ in VARIANTS:
+        r = subprocess.run([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs[tag],
+                           capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed linking {os.path.basename(lib)}")
     with open(HASH_FILE, "w") as f:
         f.write(want + "\n")
     return LIB

@@ -2,11 +2,49 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/sceneego_b200.h"
 
 namespace sceneego {
+
+// ---------------------------------------------------------------------------
+// Storage type of V2V activations and weights.  Default: bf16 (BASELINE configs[1]: "bf16 V2V").  Compiled with
+// -DSCENEEGO_ACT_F16 (libsceneego_b200_f16.so) every 16-bit cell holds IEEE fp16 instead: same tcgen05 rate
+// (kind::f16 takes either), 3 more mantissa bits -- the storage-rounding error of the 50-layer chain drops 8x
+// (profiles/r02_bf16_attribution.txt) -- at the price of fp16's range: stores saturate at +-65504 instead of
+// overflowing to infinity.  The element type in signatures stays `__nv_bfloat16` (an opaque 16-bit cell); only the
+// conversions below and the MMA instruction descriptor's A/B format bits differ.
+// ---------------------------------------------------------------------------
+#ifdef SCENEEGO_ACT_F16
+constexpr int kActDtype = 1;                               // sceneego_act_dtype()
+constexpr uint32_t kIdescAB = 0u;                          // instruction descriptor: A and B are f16
+#define SE_MMA_SYNC_AB ".f16.f16"
+__device__ __forceinline__ uint32_t act_pack2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 act_unpack2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ __nv_bfloat16 act_from_float(float v) {
+  const uint32_t r = act_pack2(v, 0.f);
+  const uint16_t lo = (uint16_t)(r & 0xFFFFu);
+  return *reinterpret_cast<const __nv_bfloat16*>(&lo);
+}
+__device__ __forceinline__ float act_to_float(__nv_bfloat16 v) { return __half2float(*reinterpret_cast<const __half*>(&v)); }
+#else
+constexpr int kActDtype = 0;
+constexpr uint32_t kIdescAB = (1u << 7) | (1u << 10);      // instruction descriptor: A and B are bf16
+#define SE_MMA_SYNC_AB ".bf16.bf16"
+__device__ __forceinline__ uint32_t act_pack2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 act_unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
+__device__ __forceinline__ __nv_bfloat16 act_from_float(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float act_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+#endif
 
 void set_error(const char* fmt, ...);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): the attribute is per device, so a

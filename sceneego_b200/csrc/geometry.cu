@@ -336,11 +336,9 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
     const int64_t cell0 = vol_cell(lay, b, vx, vy, vz, 0, C / 8);
 #pragma unroll
     for (int g = 0; g < C / 8; ++g) {
-      __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pk[q] = __floats2bfloat162_rn(acc[8 * g + 2 * q], acc[8 * g + 2 * q + 1]);
       *reinterpret_cast<uint4*>(out_bf16 + (cell0 + (int64_t)g * lay.plane_stride) * 8) =
-          *reinterpret_cast<const uint4*>(pk);
+          make_uint4(act_pack2(acc[8 * g + 0], acc[8 * g + 1]), act_pack2(acc[8 * g + 2], acc[8 * g + 3]),
+                     act_pack2(acc[8 * g + 4], acc[8 * g + 5]), act_pack2(acc[8 * g + 6], acc[8 * g + 7]));
     }
     // scene-occupancy plane(s) behind the features: cleared here, set by voxelize_kernel
     if (lay.s2d) {
@@ -377,7 +375,7 @@ struct NearestMaps {
 // One occupied voxel into the planar bf16 V2V input (three storage forms, include/sceneego_b200.h).
 __device__ __forceinline__ void set_occupied(__nv_bfloat16* __restrict__ occ, const sceneego_vol_layout_t& lay, int b, int x,
                                              int y, int z, int channel, int V) {
-  const __nv_bfloat16 one = __float2bfloat16(1.0f);
+  const __nv_bfloat16 one = act_from_float(1.0f);
   if (lay.zwin) {
     // z-window plane: entry e of cell (x,y,zc) is occ[x][y][zc-3+e] -> this voxel is entry e of the cells zc = z+3-e
     const int64_t base = ((int64_t)(channel >> 3) * lay.plane_stride + vol_pos(lay, b, x, y, 0)) * 8;
@@ -493,17 +491,17 @@ __global__ void __launch_bounds__(256) intersect_kernel(__nv_bfloat16* __restric
   if (n >= S * S * S) return;
   const int z = n % S, y = (n / S) % S, x = n / (S * S);
   const int64_t pos = vol_pos(lay, b, x, y, z);
-  const float sc = __bfloat162float(vol[((int64_t)(2 * c8) * lay.plane_stride + pos) * 8]);
+  const float sc = act_to_float(vol[((int64_t)(2 * c8) * lay.plane_stride + pos) * 8]);
   for (int g = 0; g < c8; ++g) {
     const uint4 in = *reinterpret_cast<const uint4*>(vol + ((int64_t)g * lay.plane_stride + pos) * 8);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&in);
-    __align__(16) __nv_bfloat162 o[4];
+    const uint32_t h[4] = {in.x, in.y, in.z, in.w};
+    uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 t = __bfloat1622float2(h[j]);
-      o[j] = __floats2bfloat162_rn(t.x * sc, t.y * sc);
+      const float2 t = act_unpack2(h[j]);
+      o[j] = act_pack2(t.x * sc, t.y * sc);
     }
-    *reinterpret_cast<uint4*>(vol + ((int64_t)(c8 + g) * lay.plane_stride + pos) * 8) = *reinterpret_cast<const uint4*>(o);
+    *reinterpret_cast<uint4*>(vol + ((int64_t)(c8 + g) * lay.plane_stride + pos) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -519,14 +517,14 @@ __global__ void pack_volume_kernel(const float* __restrict__ in, int c, int c_of
   const int z = n % S, y = (n / S) % S, x = n / (S * S);
   for (int ch = 0; ch < c; ++ch) {
     const int oc = ch + c_offset;
-    const __nv_bfloat16 v = __float2bfloat16(in[((size_t)b * c + ch) * S * S * S + n]);
+    const __nv_bfloat16 v = act_from_float(in[((size_t)b * c + ch) * S * S * S + n]);
     if (lay.zwin && oc >= 32) {   // z-window occupancy plane: this thread writes its whole cell = occ[x][y][z-3 .. z+4]
       if (oc == 32) {
         __align__(16) __nv_bfloat16 cell[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int zz = z - 3 + e;
-          cell[e] = __float2bfloat16((zz >= 0 && zz < S) ? in[((size_t)b * c + ch) * S * S * S + (n - z + zz)] : 0.f);
+          cell[e] = act_from_float((zz >= 0 && zz < S) ? in[((size_t)b * c + ch) * S * S * S + (n - z + zz)] : 0.f);
         }
         *reinterpret_cast<uint4*>(out + ((int64_t)4 * lay.plane_stride + vol_pos(lay, b, x, y, z)) * 8) = *reinterpret_cast<const uint4*>(cell);
       }
@@ -553,7 +551,7 @@ __global__ void unpack_volume_kernel(const __nv_bfloat16* __restrict__ in, scene
     if (lay.zwin && ch >= 32) e = ((int64_t)4 * lay.plane_stride + vol_pos(lay, b, x, y, z)) * 8 + 3;   // entry 3 = the voxel itself
     else if (lay.s2d) e = ch < 32 ? vol_cell(lay, b, x, y, z, ch >> 3, 4) * 8 + (ch & 7) : vol_scene_elem(lay, b, x, y, z, 4);
     else e = vol_cell(lay, b, x, y, z, ch >> 3, 0) * 8 + (ch & 7);
-    out[((size_t)b * c + ch) * S * S * S + n] = __bfloat162float(in[e]);
+    out[((size_t)b * c + ch) * S * S * S + n] = act_to_float(in[e]);
   }
 }
 

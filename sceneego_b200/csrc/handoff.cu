@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) handoff_pack_kernel(const float* __restri
   if (q >= plane_cells) return;
   __align__(16) __nv_bfloat16 cell[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) cell[i] = __float2bfloat16(0.f);
+  for (int i = 0; i < 8; ++i) cell[i] = act_from_float(0.f);
   const int64_t r = q - HO_GUARD;
   if (r >= 0) {
     const int b = (int)(r / frame_cells);
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) handoff_pack_kernel(const float* __restri
     if (b < batch && yp >= 1 && yp <= h && xp >= 1 && xp <= w) {
       const float* src = x + (((size_t)b * HO_CIN + 8 * g) * h + (yp - 1)) * w + (xp - 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cell[i] = __float2bfloat16(__ldg(src + (size_t)i * h * w));
+      for (int i = 0; i < 8; ++i) cell[i] = act_from_float(__ldg(src + (size_t)i * h * w));
     }
   }
   *reinterpret_cast<uint4*>(out + ((int64_t)g * plane_cells + q) * 8) = *reinterpret_cast<const uint4*>(cell);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(HO_THREADS, 1) handoff_tc_kernel(const __grid_
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = elect_one();
     const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;            // SBO = 128 B, descriptor version 1
-    constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);
+    constexpr uint32_t idesc0 = (1u << 4) | kIdescAB | (8u << 24);
     constexpr uint32_t ID256 = idesc0 | ((256u >> 3) << 17), ID32 = idesc0 | ((32u >> 3) << 17);
     const uint32_t win_plane16 = p.win_plane_bytes >> 4;
     const uint32_t a_lbo = (win_plane16 & 0x3FFFu) << 16;                  // K chunk 1 = the next channel-group plane

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(march_threads(TWO), TWO ? 2 : 1) conv_march_ke
     constexpr uint32_t tap_step = (uint32_t)(2 * KSTEPS) * 3u * N0;             // one (dy,dz) block, in 16-B units
     const uint32_t w_b = ((sbase >> 4) & 0x3FFFu) | b_lbo;
     const uint32_t w2_b = (((sbase + p.w_bytes) >> 4) & 0x3FFFu) | b2_lbo;
-    constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);   // D f32, A/B bf16 K-major, M = 128
+    constexpr uint32_t idesc0 = (1u << 4) | kIdescAB | (8u << 24);   // D f32, A/B bf16 K-major, M = 128
     constexpr uint32_t ID1 = idesc0 | ((uint32_t)(N0 >> 3) << 17), ID2 = idesc0 | ((uint32_t)(2 * N0 >> 3) << 17),
                        ID3 = idesc0 | ((uint32_t)(3 * N0 >> 3) << 17);
     const uint32_t pitch_y = (uint32_t)p.ls.pitch_y;

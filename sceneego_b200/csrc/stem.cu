@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_s2d_tc_kernel(const __gr
       if constexpr (CG == 2) tc_commit_pair(bar); else tc_commit(bar);
     };
     constexpr uint32_t NH = 128 / CG;                                      // B rows (columns of D) staged per CTA
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((CG == 2 ? 16u : 8u) << 24);
+    const uint32_t idesc = (1u << 4) | kIdescAB | ((uint32_t)(128 >> 3) << 17) | ((CG == 2 ? 16u : 8u) << 24);
     const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;            // SBO = 128 B, descriptor version 1
     const uint32_t a_lbo_feat = ((uint32_t)p.win_cells & 0x3FFFu) << 16;   // K chunk 1 = next channel-group plane
     const uint32_t a_lbo_scene = 1u << 16;                                 // K chunk 1 = next block in z (16 B)

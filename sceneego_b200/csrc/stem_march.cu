@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(SMR_THREADS, 1) stem_march_tc_kernel(const __g
     const int t = warp - 2;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = elect_one();
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (8u << 24);
+    constexpr uint32_t idesc = (1u << 4) | kIdescAB | ((uint32_t)(128 >> 3) << 17) | (8u << 24);
     const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;            // SBO = 128 B, descriptor version 1
     const uint32_t a_lbo_feat = ((uint32_t)p.win_cells & 0x3FFFu) << 16;   // K chunk 1 = the pair's second plane
     const uint32_t a_lbo_occ = ((uint32_t)pitch_y & 0x3FFFu) << 16;        // K chunk 1 = the next dy row

@@ -26,13 +26,12 @@ struct TailParams {
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32" SE_MMA_SYNC_AB ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  return act_pack2(lo, hi);
 }
 
 // B fragments of a [cin/8][cout][8] weight block: thread (g = lane/4, q = lane%4) of n-tile nt, k-tile kt holds
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_con
   // descriptors: K-major no-swizzle, SBO = 128 B between 8-row groups, LBO = distance between the two 8-channel chunks
   constexpr uint32_t DHI = 8u | (1u << 14);
   auto DESC = [](uint32_t lo) { return ((uint64_t)DHI << 32) | (uint64_t)lo; };
-  constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);
+  constexpr uint32_t idesc0 = (1u << 4) | kIdescAB | (8u << 24);
   constexpr uint32_t ID32 = idesc0 | ((32u >> 3) << 17), ID16 = idesc0 | ((16u >> 3) << 17);
   const uint32_t a_lbo = (2048u >> 4) << 16;
   auto load_tile = [&](int64_t t, int buf) {                       // issuer only
@@ -306,15 +305,15 @@ __global__ void __launch_bounds__(128) tail_mlp_simt_kernel(const __grid_constan
     const float* bias = layer ? p.b2 : p.b1;
     for (int co = 0; co < 32; ++co) {
       float acc = 0.f;
-      for (int ci = 0; ci < 32; ++ci) acc = fmaf(h[ci], __bfloat162float(w[((size_t)(ci >> 3) * 32 + co) * 8 + (ci & 7)]), acc);
-      t[co] = __bfloat162float(__float2bfloat16(fmaxf(acc + bias[co], 0.f)));
+      for (int ci = 0; ci < 32; ++ci) acc = fmaf(h[ci], act_to_float(w[((size_t)(ci >> 3) * 32 + co) * 8 + (ci & 7)]), acc);
+      t[co] = act_to_float(act_from_float(fmaxf(acc + bias[co], 0.f)));
     }
     for (int co = 0; co < 32; ++co) h[co] = t[co];
   }
   const size_t N3 = (size_t)S * S * S;
   for (int co = 0; co < p.cout_real; ++co) {
     float acc = 0.f;
-    for (int ci = 0; ci < 32; ++ci) acc = fmaf(h[ci], __bfloat162float(p.w3[((size_t)(ci >> 3) * 16 + co) * 8 + (ci & 7)]), acc);
+    for (int ci = 0; ci < 32; ++ci) acc = fmaf(h[ci], act_to_float(p.w3[((size_t)(ci >> 3) * 16 + co) * 8 + (ci & 7)]), acc);
     p.dst[((size_t)b * p.cout_real + co) * N3 + n] = acc + p.b3[co];
   }
 }

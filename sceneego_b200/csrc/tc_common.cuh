@@ -159,26 +159,41 @@ static inline FastDiv make_fastdiv(uint32_t d) { FastDiv f; f.d = d; f.m = (1ull
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)n * f.m) >> 48); }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
+    const float2 t = act_unpack2(w[i]);
     f[2 * i] = t.x; f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  __align__(16) __nv_bfloat162 h[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return *reinterpret_cast<const uint4*>(h);
+  return make_uint4(act_pack2(f[0], f[1]), act_pack2(f[2], f[3]), act_pack2(f[4], f[5]), act_pack2(f[6], f[7]));
 }
 
-static inline uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+// Host-side conversion of a folded weight to the storage type (round-to-nearest-even, like the device conversions).
+static inline uint16_t f2bf(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
+#ifdef SCENEEGO_ACT_F16
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                 // NaN
+  if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);                // >= 65520 rounds past the largest half: saturate
+  if (a < 0x33000001u) return (uint16_t)sign;                             // < 2^-25: rounds to zero
+  int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;
+  int shift = e < -14 ? 13 + (-14 - e) : 13;                              // subnormal halves lose more bits
+  const uint32_t halfway = 1u << (shift - 1), mask = (1u << shift) - 1u;
+  uint32_t r = m >> shift;
+  const uint32_t rem = m & mask;
+  if (rem > halfway || (rem == halfway && (r & 1u))) ++r;
+  const uint32_t bits = e < -14 ? r : (((uint32_t)(e + 15) << 10) + (r - 0x400u));   // a mantissa carry bumps the exponent
+  return (uint16_t)(sign | bits);
+#else
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
+#endif
 }
 
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB

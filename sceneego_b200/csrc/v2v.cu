@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(conv_threads(TILES), 1) conv_tc_kernel(const _
       if constexpr (CG == 2) tc_commit_pair(bar); else tc_commit(bar);
     };
     // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128 (256 over a CTA pair), N=p.mma_n
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.mma_n >> 3) << 17) | ((CG == 2 ? 16u : 8u) << 24);
+    const uint32_t idesc = (1u << 4) | kIdescAB | ((uint32_t)(p.mma_n >> 3) << 17) | ((CG == 2 ? 16u : 8u) << 24);
     // K-major no-swizzle: LBO = byte stride between the two 8-channel K chunks of one MMA,
     // SBO = byte stride between 8-row core matrices (validated on B200 hardware).
     // hi word: SBO = 128 B (>>4 = 8) | descriptor version 1 (bit 46 -> bit 14 of the hi word)
@@ -906,6 +906,7 @@ static int plan_conv(ConvParams& p, int64_t n_pos) {
 using namespace sceneego;
 
 extern "C" int sceneego_abi_version(void) { return SCENEEGO_ABI_VERSION; }
+extern "C" int sceneego_act_dtype(void) { return kActDtype; }
 extern "C" const char* sceneego_last_error(void) { return g_err; }
 extern "C" int sceneego_v2v_last_launch_count(void) { return g_launches; }
 

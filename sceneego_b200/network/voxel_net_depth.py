@@ -43,7 +43,7 @@ def _resolve_calibration(path):
 class VoxelNetwork_depth(nn.Module):
     def __init__(self, config, device='cuda', materialize_features=True, materialize_volumes=True,
                  fused_projection=False, v2v_chunk=32, persistent_features=False, graph_max_batch=0,
-                 backbone_handoff=False):
+                 backbone_handoff=False, act_dtype=None):
         """Extra keyword switches (all default to reference-identical outputs):
         materialize_features / materialize_volumes: build outputs #2 / #3 of the reference
             forward (168 MB and 15.7 MB per frame, ignored by demo.py:57 / test.py:54);
@@ -56,11 +56,16 @@ class VoxelNetwork_depth(nn.Module):
             (demo.py runs batch 1: ~70 launches of a few microseconds each are launch-bound otherwise); 0 = off.
         backbone_handoff: forward() fuses the backbone's last deconvolution stage (ConvTranspose2d + BN + ReLU) with
             process_features[0] in one tensor-core kernel (bf16 operands, fp32 accumulation) instead of running the
-            stage in torch and the 1x1 conv in fp32; `lift()` is unaffected."""
+            stage in torch and the 1x1 conv in fp32; `lift()` is unaffected.
+        act_dtype: "bf16" (default) or "f16" -- storage type of the V2V activations and packed weights.  "f16" loads
+            libsceneego_b200_f16.so (same kernels, IEEE fp16 cells with saturating stores): same speed, 8-9x smaller
+            storage-rounding error (33.9 -> 3.7 mm in the sharp-softmax test).  One dtype per process."""
         super().__init__()
         dev = torch.device(device)
         if dev.type != 'cuda':
             raise _lib.SceneEgoError("sceneego_b200.VoxelNetwork_depth needs a CUDA device (no CPU fallback)")
+        if act_dtype is not None:
+            _lib.set_act_dtype(act_dtype)
         _lib.load_library()
         dev = _lib._as_device(dev)
         self.device = device

@@ -54,3 +54,20 @@ def test_cpu_tensors_are_rejected():
     import torch
     with pytest.raises(_lib.SceneEgoError):
         _lib._ptr(torch.zeros(4))
+
+
+def test_fp16_storage_library_loads_and_packs():
+    """libsceneego_b200_f16.so (the same sources with -DSCENEEGO_ACT_F16) exports the same symbols, reports its storage
+    type, and its host-side packers -- fold, fp16 round-to-nearest-even with saturation, the marching / stem / hand-off
+    layouts walked like the kernels walk them -- pass the host-logic suite (one dtype per process: a subprocess)."""
+    import subprocess
+    import sys
+    f16 = ctypes.CDLL(_lib.LIB_PATHS["f16"])
+    bf = ctypes.CDLL(_lib.LIB_PATHS["bf16"])
+    for n in _declared():
+        assert hasattr(f16, n), n
+    assert f16.sceneego_act_dtype() == 1 and bf.sceneego_act_dtype() == 0
+    env = dict(os.environ, SCENEEGO_ACT_DTYPE="f16", PYTHONPATH=util.ROOT)
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_host_logic.py", "-q", "-x"], cwd=util.ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]

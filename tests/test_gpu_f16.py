@@ -1,0 +1,43 @@
+"""The fp16-storage build of the library (libsceneego_b200_f16.so = the same sources with -DSCENEEGO_ACT_F16):
+V2V activations and packed weights as IEEE fp16 with saturating stores instead of bf16.  Same tensor-core rate
+(tcgen05 kind::f16 takes either), 3 more mantissa bits: the storage-rounding error of the chain drops ~8x, which is
+what the sharp-softmax regime (output layer x30) needs (profiles/r02_bf16_attribution.txt).  One activation dtype per
+process, so these checks run in subprocesses with SCENEEGO_ACT_DTYPE=f16."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(args, timeout=900):
+    env = dict(os.environ, SCENEEGO_ACT_DTYPE="f16", PYTHONPATH=util.ROOT)
+    return subprocess.run([sys.executable] + args, cwd=util.ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_stage_with_fp16_storage_vs_reference():
+    r = _run(["-m", "tests.f16_stage_check"])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("F16CHECK ")][-1]
+    out = json.loads(line[len("F16CHECK "):])
+    print(json.dumps(out))
+    assert out["dtype"] == "f16" and out["occupancy_bit_exact"] and out["saturates_at"] == 65504.0
+    for tag in ("default_s1", "random_bn_s1"):
+        assert out[tag]["mpjpe_mm"] <= 0.05                      # bf16: 0.06 / 0.11 mm
+        assert out[tag]["logits_rel_fro"] <= 2.5e-3 and out[tag]["logits_max_over_range"] <= 2e-3     # bf16: 6-8e-3 / 4-5e-3
+    assert out["random_bn_s30"]["mpjpe_mm"] <= 10.0              # bf16: 33.9 mm; emulation predicts 4.0 mm
+    assert out["random_bn_s30"]["logits_rel_fro"] <= 2.5e-3
+
+
+def test_kernel_parity_suite_with_fp16_storage():
+    """The per-kernel parity tests (vs torch fp32, vs the CUDA-core checkers, pads, determinism) on the fp16 build:
+    marching stem, marching convs, conv_tc incl. CTA pairs and fused shortcuts, transposed convs, pool, tail."""
+    r = _run(["-m", "pytest", "tests/test_gpu_v2v.py", "-m", "gpu", "-x", "-q"], timeout=1500)
+    tail = (r.stdout + r.stderr)[-1500:]
+    assert r.returncode == 0, tail
+    print(tail.splitlines()[-1])

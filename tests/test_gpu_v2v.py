@@ -70,8 +70,8 @@ CASES = [
 def test_single_conv(cin, cout, k, S, B, pad_src, impl):
     conv, bn = _mk_conv(cin, cout, k, seed=cin * 1000 + cout * 10 + k)
     g = torch.Generator().manual_seed(S + B)
-    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
-    res = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
+    x = util.act_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    res = util.act_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
     got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=res, impl=impl, pad_src=pad_src)
     _close(got, _ref(x, conv, bn, True, res=res), f"conv {cin}->{cout} k{k} S{S} impl{impl}")
     # pad cells of the destination must be exactly zero (they are the next layer's padding)
@@ -93,8 +93,8 @@ def test_x_stacked_conv(cin, cout, k, S, B, pad_src, xs):
     """x-stacking: GEMM rows produce `xs` consecutive x-planes against Toeplitz-stacked weights."""
     conv, bn = _mk_conv(cin, cout, k, seed=99 + xs)
     g = torch.Generator().manual_seed(S * 7 + B)
-    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
-    res = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
+    x = util.act_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    res = util.act_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
     got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, pad_src=pad_src, xstack=xs)
     _close(got, _ref(x, conv, bn, True, res=res), f"xstack{xs} conv {cin}->{cout} k{k} S{S}")
     plain, _, _ = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, pad_src=pad_src, xstack=1)
@@ -118,8 +118,8 @@ def test_cta_pair_conv(cin, cout, k, S, B, xs):
     Same math as the single-CTA kernel on the same inputs (odd item counts repeat the last item)."""
     conv, bn = _mk_conv(cin, cout, k, seed=17 + xs)
     g = torch.Generator().manual_seed(S * 3 + B)
-    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
-    res = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
+    x = util.act_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    res = util.act_round(torch.randn(B, cout, S, S, S, generator=g)).cuda()
     got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, xstack=xs, cta_pair=2)
     _close(got, _ref(x, conv, bn, True, res=res), f"cta pair conv {cin}->{cout} k{k} S{S}")
     one, _, _ = util.run_single_op(x, conv, bn, relu=True, res=res, impl=0, xstack=xs, cta_pair=1)
@@ -143,8 +143,8 @@ def test_fused_projection_shortcut(c, S, B, xs, pair):
     conv, bn = _mk_conv(c, c, 3, seed=3 * c)
     sc_conv, sc_bn = _mk_conv(c // 2, c, 1, seed=5 * c)
     g = torch.Generator().manual_seed(S + B + c)
-    t_in = util.bf16_round(torch.randn(B, c, S, S, S, generator=g)).cuda()
-    x_in = util.bf16_round(torch.randn(B, c // 2, S, S, S, generator=g)).cuda()
+    t_in = util.act_round(torch.randn(B, c, S, S, S, generator=g)).cuda()
+    x_in = util.act_round(torch.randn(B, c // 2, S, S, S, generator=g)).cuda()
     got, dst, lay = util.run_single_op(t_in, conv, bn, relu=True, impl=0, xstack=xs, cta_pair=pair,
                                        shortcut=(sc_conv, sc_bn, x_in))
     with torch.no_grad():
@@ -184,8 +184,8 @@ def test_marching_conv(cin, cout, S, B, res):
     360 / 630 items on 296 CTAs: whole rounds of interleaved items plus a last round cut by planes)."""
     conv, bn = _mk_conv(cin, cout, 3, seed=31 + cin + S)
     g = torch.Generator().manual_seed(S * 5 + B)
-    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
-    r = util.bf16_round(torch.randn(B, cout, S, S, S, generator=g)).cuda() if res else None
+    x = util.act_round(torch.randn(B, cin, S, S, S, generator=g)).cuda()
+    r = util.act_round(torch.randn(B, cout, S, S, S, generator=g)).cuda() if res else None
     got, dst, lay = util.run_single_op(x, conv, bn, relu=True, res=r, impl=0, march=True)
     _close(got, _ref(x, conv, bn, True, res=r), f"marching conv {cin}->{cout} S{S}")
     simt, _, _ = util.run_single_op(x, conv, bn, relu=True, res=r, impl=1, march=True)
@@ -201,8 +201,8 @@ def test_marching_conv_fused_shortcut(S, B):
     conv, bn = _mk_conv(32, 32, 3, seed=77)
     sc_conv, sc_bn = _mk_conv(16, 32, 1, seed=78)
     g = torch.Generator().manual_seed(S + B)
-    t_in = util.bf16_round(torch.randn(B, 32, S, S, S, generator=g)).cuda()
-    x_in = util.bf16_round(torch.randn(B, 16, S, S, S, generator=g)).cuda()
+    t_in = util.act_round(torch.randn(B, 32, S, S, S, generator=g)).cuda()
+    x_in = util.act_round(torch.randn(B, 16, S, S, S, generator=g)).cuda()
     got, dst, lay = util.run_single_op(t_in, conv, bn, relu=True, impl=0, march=True, shortcut=(sc_conv, sc_bn, x_in))
     with torch.no_grad():
         ref = F.relu(bn(conv(t_in)) + sc_bn(sc_conv(x_in)))
@@ -218,8 +218,8 @@ def test_marching_conv_single_cta_per_sm_variant():
     import os
     conv, bn = _mk_conv(32, 32, 3, seed=9)
     g = torch.Generator().manual_seed(4)
-    x = util.bf16_round(torch.randn(3, 32, 24, 24, 24, generator=g)).cuda()
-    r = util.bf16_round(torch.randn(3, 32, 24, 24, 24, generator=g)).cuda()
+    x = util.act_round(torch.randn(3, 32, 24, 24, 24, generator=g)).cuda()
+    r = util.act_round(torch.randn(3, 32, 24, 24, 24, generator=g)).cuda()
     two, _, _ = util.run_single_op(x, conv, bn, relu=True, res=r, impl=0, march=True)
     os.environ["SCENEEGO_MARCH_CTAS"] = "1"
     try:
@@ -234,7 +234,7 @@ def test_marching_conv_single_cta_per_sm_variant():
 def test_marching_conv_is_deterministic_and_reuses_buffers():
     """Two runs over the same buffers give bit-identical results (one issuer, fixed accumulation order)."""
     conv, bn = _mk_conv(32, 32, 3, seed=5)
-    x = util.bf16_round(torch.randn(4, 32, 32, 32, 32, generator=torch.Generator().manual_seed(2))).cuda()
+    x = util.act_round(torch.randn(4, 32, 32, 32, 32, generator=torch.Generator().manual_seed(2))).cuda()
     a, _, _ = util.run_single_op(x, conv, bn, relu=True, impl=0, march=True)
     b, _, _ = util.run_single_op(x, conv, bn, relu=True, impl=0, march=True)
     assert torch.equal(a, b)
@@ -249,7 +249,7 @@ def test_stem_march(V, B):
     from sceneego_b200 import _lib
     conv, bn = _mk_conv(33, 16, 7, seed=5)
     g = torch.Generator().manual_seed(V + B)
-    x = util.bf16_round(torch.randn(B, 33, V, V, V, generator=g))
+    x = util.act_round(torch.randn(B, 33, V, V, V, generator=g))
     x[:, 32] = (x[:, 32] > 0.8).float()                       # occupancy channel is {0,1}
     x = x.cuda()
     got, dst, lay, src, lay_s = util.run_stem_s2d(x, conv, bn, impl=0, kind="march")
@@ -281,7 +281,7 @@ def test_stem_s2d(V, B, pair):
     from sceneego_b200 import _lib
     conv, bn = _mk_conv(33, 16, 7, seed=5)
     g = torch.Generator().manual_seed(V + B)
-    x = util.bf16_round(torch.randn(B, 33, V, V, V, generator=g))
+    x = util.act_round(torch.randn(B, 33, V, V, V, generator=g))
     x[:, 32] = (x[:, 32] > 0.8).float()                       # occupancy channel is {0,1}
     x = x.cuda()
     got, dst, lay, src, lay_s = util.run_stem_s2d(x, conv, bn, impl=0, cta_pair=pair)
@@ -304,7 +304,7 @@ def test_tc_matches_simt_bitwise_close(cin, cout, S, B):
     """Same packed weights, same bf16 inputs: tensor-core and CUDA-core paths may differ only
     by fp32 accumulation order, i.e. at most one bf16 ulp after the output rounding."""
     conv, bn = _mk_conv(cin, cout, 3, seed=7)
-    x = util.bf16_round(torch.randn(B, cin, S, S, S, generator=torch.Generator().manual_seed(1))).cuda()
+    x = util.act_round(torch.randn(B, cin, S, S, S, generator=torch.Generator().manual_seed(1))).cuda()
     a, _, _ = util.run_single_op(x, conv, bn, relu=False, impl=0)
     b, _, _ = util.run_single_op(x, conv, bn, relu=False, impl=1)
     assert ((a - b).abs() <= 0.0079 * b.abs() + 1e-4).all()
@@ -314,7 +314,7 @@ def test_maxpool_and_deconv():
     from sceneego_b200 import _lib
     import ctypes as C
     S, B, c = 16, 2, 64
-    x = util.bf16_round(torch.randn(B, c, S, S, S, generator=torch.Generator().manual_seed(3))).cuda()
+    x = util.act_round(torch.randn(B, c, S, S, S, generator=torch.Generator().manual_seed(3))).cuda()
     lay_s, lay_d = _lib.vol_layout(S, 1, B), _lib.vol_layout(S // 2, 1, B)
     src, dst = _lib.alloc_volume(lay_s, c, x.device), _lib.alloc_volume(lay_d, c, x.device)
     _lib.pack_volume(x, src, lay_s)
@@ -331,8 +331,8 @@ def test_maxpool_and_deconv():
 
     for cin, cout, s in ((64, 32, 8), (128, 128, 2), (128, 64, 4)):
         conv, bn = _mk_conv(cin, cout, 2, seed=11, transposed=True)
-        x = util.bf16_round(torch.randn(B, cin, s, s, s, generator=torch.Generator().manual_seed(4))).cuda()
-        skip = util.bf16_round(torch.randn(B, cout, 2 * s, 2 * s, 2 * s, generator=torch.Generator().manual_seed(5))).cuda()
+        x = util.act_round(torch.randn(B, cin, s, s, s, generator=torch.Generator().manual_seed(4))).cuda()
+        skip = util.act_round(torch.randn(B, cout, 2 * s, 2 * s, 2 * s, generator=torch.Generator().manual_seed(5))).cuda()
         got, _, _ = util.run_single_op(x, conv, bn, relu=True, deconv=True, add_after=skip)
         _close(got, _ref(x, conv, bn, True, add_after=skip), f"deconv {cin}->{cout}")
 

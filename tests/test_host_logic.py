@@ -65,7 +65,7 @@ def test_program_structure_and_flops():
 
 def _unpack(w_packed, taps, cin_pad, cout_pad):
     a = w_packed.reshape(taps, cin_pad // 8, cout_pad, 8)
-    f = (a.astype(np.uint32) << 16).view(np.float32)
+    f = util.decode_act(a)
     return f.transpose(2, 1, 3, 0).reshape(cout_pad, cin_pad, taps)     # (co, ci, tap)
 
 
@@ -90,11 +90,11 @@ def test_pack_conv_folds_batchnorm():
         if tr:   # transposed: parities stacked along N in groups of npar = min(8, 256 / cout_pad)
             npar = min(8, 256 // cout_p)
             a = wp.reshape(taps // npar, cin_p // 8, npar, cout_p, 8)
-            f = (a.astype(np.uint32) << 16).view(np.float32)
+            f = util.decode_act(a)
             got = f.transpose(3, 1, 4, 0, 2).reshape(cout_p, cin_p, taps)
         else:
             got = _unpack(wp, taps, cin_p, cout_p)
-        ref = torch.from_numpy(wf.astype(np.float32)).to(torch.bfloat16).float().numpy()
+        ref = util.act_round(torch.from_numpy(wf.astype(np.float32))).numpy()
         assert np.array_equal(got[:cout, :cin], ref)                 # bf16 round-to-nearest-even, bit-exact
         assert np.all(got[cout:] == 0) and np.all(got[:, cin:] == 0)  # channel padding is zero
         assert np.allclose(bp[:cout], b * scale + (beta - mean * scale), rtol=1e-6, atol=1e-6)
@@ -155,7 +155,7 @@ def test_stem_s2d_packing_reproduces_conv3d():
     ptrs = [k.ctypes.data_as(C.c_void_p) for k in keep]
     assert lib.sceneego_v2v_pack_stem_s2d(*ptrs, C.c_double(bn.eps), 1, w_out.ctypes.data_as(C.c_void_p),
                                           b_out.ctypes.data_as(C.c_void_p)) == 0
-    wf = torch.from_numpy((w_out.astype(np.uint32) << 16).view(np.float32).copy()).double()   # bf16 -> f64
+    wf = torch.from_numpy(util.decode_act(w_out).copy()).double()   # storage type -> f64
     V, S2, P = 8, 4, 2
     x = torch.randn(33, V, V, V).double()
     x[32] = (x[32] > 0.5).double()
@@ -214,7 +214,7 @@ def test_stem_march_packing_walked_like_the_kernel_reproduces_conv3d():
     ptrs = [k.ctypes.data_as(C.c_void_p) for k in keep]
     assert lib.sceneego_v2v_pack_stem_march(*ptrs, C.c_double(bn.eps), w_out.ctypes.data_as(C.c_void_p),
                                             b_out.ctypes.data_as(C.c_void_p)) == 0
-    wf = torch.from_numpy((w_out.astype(np.uint32) << 16).view(np.float32).copy()).double()
+    wf = torch.from_numpy(util.decode_act(w_out).copy()).double()
     ROT, FEAT, MMA = 417792 // 2, 28672 // 2, 4096 // 2                    # elements
     assert wf.numel() == 8 * ROT
     S, P = 6, 3
@@ -286,7 +286,7 @@ def test_march_packing_walked_like_the_kernel_reproduces_conv3d():
     args = [a.ctypes.data_as(C.c_void_p) for a in keep]
     assert lib.sceneego_v2v_pack_conv_march(*args, C.c_double(bn.eps), cout, cin, cout, cin,
                                             w_out.ctypes.data_as(C.c_void_p), b_out.ctypes.data_as(C.c_void_p)) == 0
-    wf = (w_out.astype(np.uint32) << 16).view(np.float32).reshape(9, cin // 8, 3 * cout, 8)     # [t][g][row][c8]
+    wf = util.decode_act(w_out).reshape(9, cin // 8, 3 * cout, 8)     # [t][g][row][c8]
     wm = wf.transpose(0, 2, 1, 3).reshape(9, 3 * cout, cin).astype(np.float64)                  # [t][row][ci]
     x = torch.randn(1, cin, S, S, S).to(torch.bfloat16).float()
     xp = np.zeros((cin, S, S + 2, S + 2))
@@ -313,7 +313,7 @@ def test_march_packing_walked_like_the_kernel_reproduces_conv3d():
     out += b_out.astype(np.float64)[:, None, None, None]
     with torch.no_grad():
         wq = conv.weight * (bn.weight / torch.sqrt(bn.running_var + bn.eps))[:, None, None, None, None]
-        ref = F.conv3d(x.double(), wq.to(torch.bfloat16).double(), padding=1)[0].numpy()
+        ref = F.conv3d(x.double(), util.act_round(wq).double(), padding=1)[0].numpy()
         ref += ((conv.bias - bn.running_mean) * bn.weight / torch.sqrt(bn.running_var + bn.eps) + bn.bias).double().numpy()[:, None, None, None]
     assert np.abs(out - ref).max() <= 1e-5
 

@@ -126,3 +126,19 @@ def run_stem_s2d(x, conv, bn, impl=0, cta_pair=1, kind="s2d"):
 
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
+
+
+def decode_act(a):
+    """uint16 array of packed weights / activations -> float32, in the library's 16-bit storage type
+    (bf16 by default, IEEE fp16 under SCENEEGO_ACT_DTYPE=f16)."""
+    from sceneego_b200 import _lib
+    a = np.ascontiguousarray(a)
+    if _lib.act_dtype_name() == "f16":
+        return a.view(np.float16).astype(np.float32)
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def act_round(t):
+    """Round a float tensor to the library's 16-bit storage type and back."""
+    from sceneego_b200 import _lib
+    return t.to(_lib.act_torch_dtype()).to(torch.float32)
