@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for sm in 0 12000 20000 40000; do
+  SCENEEGO_UPSAMPLE_SMEM=$sm timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-kernel-table --out gpurun_out/r02_upsample_throttle.jsonl > /dev/null 2>&1
+done
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-kernel-table --no-features --out gpurun_out/r02_upsample_throttle.jsonl > /dev/null 2>&1
+python - <<'PY'
+import json
+for l in open('gpurun_out/r02_upsample_throttle.jsonl'):
+    d=json.loads(l); print('value %.0f'%d['value'], 'ms %.3f'%d['ms_per_step'], d['config']['outputs'][:40])
+PY
