@@ -406,3 +406,30 @@ def test_second_device_without_set_device(tables64):
         b = n1.lift(feat.to("cuda:1"), n1.grid_coord_proj_batch, n1.coord_volumes, depth_map_batch=depth.to("cuda:1"))[0]
     assert b.device == torch.device("cuda", 1) and torch.cuda.current_device() == 0
     assert torch.equal(a.cpu(), b.cpu())
+
+
+def test_stage_v96_non_power_of_two_cube_vs_oracle():
+    """volume_size = 96 (divisible by 32 as the five poolings need, NOT a power of two: the index decodes of the gather,
+    the soft-argmax and the marching stem's x-segments take their generic branches): whole stage, B = 2, against the
+    CPU oracle run here (no reference-generated golden at this size; the oracle is pinned at 64 and 128)."""
+    from sceneego_b200.network.voxel_net_depth import VoxelNetwork_depth
+    torch.manual_seed(0)
+    net96 = VoxelNetwork_depth(util.load_config(batch_size=2, volume_size=96), device="cuda", v2v_chunk=2).eval()
+    sd = _load(net96, "random_bn", 1.0)
+    t96 = orc.StageTables(util.CALIB, 96, 2.0)
+    feat = synth.synthetic_features(2, seed=61)
+    depth = synth.synthetic_depth_room(2, t96.ray, seed=62)
+    net96.keep_logits = True
+    with torch.no_grad():
+        kp, _, volumes, _ = net96.lift(feat.cuda(), net96.grid_coord_proj_batch, net96.coord_volumes, depth_map_batch=depth.cuda())
+        kp_ref, _, vol_ref, inter = orc.stage_forward(t96, sd, feat[:1], depth_batch=depth[:1], return_intermediates=True)
+    err_mm = orc.mpjpe(kp[:1].cpu().numpy(), kp_ref.numpy()) * 1000.0
+    lg = inter["logits"]
+    rel = ((net96.last_logits[:1].cpu() - lg).norm() / lg.norm()).item()
+    print(f"[V=96] MPJPE vs oracle {err_mm:.4f} mm; logits rel-Frobenius {rel:.3e}")
+    assert err_mm <= 0.5 and rel <= LOGIT_REL_FRO
+    pg = net96.volume_net.program(96, 2, torch.device("cuda", 0))
+    from sceneego_b200 import _lib
+    occ = _lib.unpack_volume(pg.buffers[pg.in_buf], pg.lay_in, 2, 33)[0, 32]
+    assert torch.equal(occ.cpu(), inter["scene"][0])
+    del net96
