@@ -36,8 +36,10 @@ def test_stage_with_fp16_storage_vs_reference():
 
 def test_kernel_parity_suite_with_fp16_storage():
     """The per-kernel parity tests (vs torch fp32, vs the CUDA-core checkers, pads, determinism) on the fp16 build:
-    marching stem, marching convs, conv_tc incl. CTA pairs and fused shortcuts, transposed convs, pool, tail."""
-    r = _run(["-m", "pytest", "tests/test_gpu_v2v.py", "-m", "gpu", "-x", "-q"], timeout=1500)
+    marching stem, marching convs, conv_tc incl. CTA pairs and fused shortcuts, transposed convs, pool, tail, and the
+    backbone hand-off kernel (A operand of its second GEMM read from tensor memory as fp16)."""
+    r = _run(["-m", "pytest", "tests/test_gpu_v2v.py", "tests/test_gpu_handoff.py", "-k", "not forward_with_backbone", "-m", "gpu", "-x", "-q"],
+             timeout=1500)
     tail = (r.stdout + r.stderr)[-1500:]
     assert r.returncode == 0, tail
     print(tail.splitlines()[-1])

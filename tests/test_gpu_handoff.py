@@ -33,7 +33,7 @@ def _modules(seed):
 def test_handoff_kernel_vs_torch_fp32(B, h, w):
     """deconv(k4,s2,p1) + BN + ReLU + 1x1 conv as one tcgen05 kernel vs the same ops in torch fp32 (TF32 off).
     bf16 operands with fp32 accumulation: 5e-3 relative Frobenius; against the same computation with the operands
-    rounded like the kernel rounds them (input, folded weights, hidden activations, 1x1 weights) 1e-3 of the range."""
+    rounded like the kernel rounds them (bf16, or fp16 on the fp16-storage build) (input, folded weights, hidden activations, 1x1 weights) 1e-3 of the range."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dc, bn, pf = _modules(7)
@@ -46,12 +46,12 @@ def test_handoff_kernel_vs_torch_fp32(B, h, w):
         rel = ((got - ref).norm() / ref.norm()).item()
         # the kernel's own roundings, emulated
         sc = (bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps))
-        w1 = util.bf16_round((dc.weight.double() * sc.view(1, -1, 1, 1)).float())
+        w1 = util.act_round((dc.weight.double() * sc.view(1, -1, 1, 1)).float())
         sh = (bn.bias.double() - bn.running_mean.double() * sc).float()
-        hid = util.bf16_round(F.relu(F.conv_transpose2d(util.bf16_round(x), w1, None, stride=2, padding=1) + sh.view(1, -1, 1, 1)))
-        emu = (F.conv2d(hid, util.bf16_round(pf.weight), pf.bias)).permute(0, 2, 3, 1).contiguous()
+        hid = util.act_round(F.relu(F.conv_transpose2d(util.act_round(x), w1, None, stride=2, padding=1) + sh.view(1, -1, 1, 1)))
+        emu = (F.conv2d(hid, util.act_round(pf.weight), pf.bias)).permute(0, 2, 3, 1).contiguous()
     err = ((got - emu).abs().max() / (emu.max() - emu.min())).item()
-    print(f"handoff B={B} {h}x{w}: rel-Frobenius vs fp32 {rel:.3e}, max-abs/range vs bf16-emulation {err:.3e}")
+    print(f"handoff B={B} {h}x{w}: rel-Frobenius vs fp32 {rel:.3e}, max-abs/range vs 16-bit emulation {err:.3e}")
     assert rel <= 5e-3 and err <= 1e-3
     again = _lib.backbone_handoff(x, wts, bias)
     assert torch.equal(again, got)
