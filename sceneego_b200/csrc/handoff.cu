@@ -10,25 +10,27 @@
 // are 128 consecutive positions and the A operand of a tap is the staged window at a shifted start address -- the
 // same construction as the 3-D kernels.  Per 128-row tile and parity:
 //     GEMM 1: 4 taps x 16 K-steps of N256 K16 (weights streamed from L2, BN scale folded in)   -> 256 TMEM columns
-//     epilogue 1: + BN shift, ReLU, bf16 -> the 128 x 256 hidden tile in shared memory (never in HBM)
-//     GEMM 2: 16 K-steps of N32 K16 against the resident 1x1 weights -> the first 32 of the columns just drained
+//     epilogue 1: + BN shift, ReLU, bf16 -> the 128 x 256 hidden tile, packed back into the tensor-memory columns just read
+//     GEMM 2: 16 K-steps of N32 K16, A operand FROM TENSOR MEMORY, against the resident 1x1 weights -> 32 drained columns
 //     epilogue 2: + bias, f32 -> out[b][2Y+a][2X+b][0..31] (128 contiguous bytes per pixel)
-// Round-2 form (the first one ran at 0.38 of the cuBLAS peak: five 8 KB weight slots in flight against an L2 round trip
-// of ~1.7k cycles, and the four phases of a parity back to back):
-//   * the hidden tile never touches shared memory: epilogue 1 packs it as bf16 into the first 128 columns of the
-//     accumulator half it has just drained (tcgen05.st) and GEMM 2 takes its A operand from tensor memory; the 64 KB
-//     this frees go to the weight ring (13 x 8 KB in flight);
-//   * CTAs run in clusters of two and each loads HALF of every weight chunk, multicast into both (cp.async.bulk
-//     .multicast::cluster): half the L2 reads per MMA;
+// What the round-2 form does, and why (the first form -- hidden tile in shared memory, five 8 KB weight slots, the four
+// phases of a parity back to back -- ran at 0.38 of the cuBLAS burst peak; history in profiles/r02_ncu_handoff_b64.txt):
+//   * the hidden tile never touches shared memory (tcgen05.st over the accumulator half just drained; GEMM 2 reads it
+//     as its A operand); the 64 KB this frees go to the weight ring (6 x 16 KB in flight against a ~1.7k-cycle L2
+//     round trip at 64 B/clk per SM);
 //   * the two 256-column halves of tensor memory alternate between parities, and GEMM 2 of parity k-1 is issued in
-//     the middle of GEMM 1 of parity k, so both epilogues run under the next parity's MMAs.
-//   (CTA-pair MMAs -- cta_group::2, weights N-split -- were tried first: every pair instruction, MMA or commit, keeps
-//   its issuing warp for ~222 cycles, so one issuer cannot feed 128-cycle MMAs; measured 0.21 ms against 0.22.)
+//     the middle of GEMM 1 of parity k, so both epilogues run under the next parity's MMAs;
+//   * CTAs run in clusters of two and each loads HALF of every weight chunk, multicast into both (cp.async.bulk
+//     .multicast::cluster): half the L2 reads, same speed (SCENEEGO_HANDOFF_MULTICAST=0 turns it off);
+//   * the issuing warp's loop is registers only -- no kernel-parameter loads, K unrolled, one wait and one commit per
+//     two MMAs: at ~55 instructions per MMA it, not the memory system, paced the first forms at ~350 cycles per MMA.
+//   (CTA-pair MMAs -- cta_group::2, weights N-split -- do not work here: every pair instruction, MMA or commit, keeps
+//   its issuing warp for ~222 cycles, and one accumulator per CTA leaves room for one issuer only.)
 // warp 0 = producer (cp.async.bulk: the 32-plane window once per tile, weight chunks), warp 1 = MMA issuer,
 // warps 2..5 = epilogue (the four tensor-memory lane quarters).
 #include "tc_common.cuh"
 #include <math.h>
-#include <stdlib.h>
+#include <stdlib.h>    // getenv
 
 namespace sceneego {
 
