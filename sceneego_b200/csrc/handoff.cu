@@ -26,6 +26,8 @@
 //     two MMAs: at ~55 instructions per MMA it, not the memory system, paced the first forms at ~350 cycles per MMA.
 //   (CTA-pair MMAs -- cta_group::2, weights N-split -- do not work here: every pair instruction, MMA or commit, keeps
 //   its issuing warp for ~222 cycles, and one accumulator per CTA leaves room for one issuer only.)
+//   * the window is loaded in two K halves and the K loop of a parity runs half-major, so the next tile's window
+//     lands under MMAs of the current one (no bubble between tiles).
 // warp 0 = producer (cp.async.bulk: the 32-plane window once per tile, weight chunks), warp 1 = MMA issuer,
 // warps 2..5 = epilogue (the four tensor-memory lane quarters).
 #include "tc_common.cuh"
@@ -46,7 +48,7 @@ constexpr int HO_W_SLOTS = 6;                                // 96 KB in flight
 constexpr int HO_W1_BYTES = HO_CHUNKS * HO_CHUNK_BYTES;                  // 2 MB
 constexpr int HO_W2_BYTES = (HO_MID / 16) * 2 * HO_OUT * 16;             // [K-step 16][2][32 rows][8] = 16 KB
 constexpr int HO_GUARD = 40;
-constexpr int HO_BARRIERS = 2 + 2 * HO_W_SLOTS + 2 + 2 + 1 + 1;          // window, weight ring, accumulator halves, hidden tile, GEMM 2
+constexpr int HO_BARRIERS = 4 + 2 * HO_W_SLOTS + 2 + 2 + 1 + 1;          // window halves, weight ring, accumulator halves, hidden tile, GEMM 2
 
 struct HandoffParams {
   const __nv_bfloat16* x;     // planar zero-bordered input, HO_PLANES planes of plane_cells cells
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(HO_THREADS, 1) handoff_tc_kernel(const __grid_
   float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
   const uint32_t bar0 = sbase + p.off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_WIN_FULL = 0, B_WIN_EMPTY = 1, B_W_FULL = 2, B_W_EMPTY = B_W_FULL + HO_W_SLOTS, B_TM1_FULL = B_W_EMPTY + HO_W_SLOTS,
+  constexpr int B_WIN_FULL = 0, B_WIN_EMPTY = 2, B_W_FULL = 4, B_W_EMPTY = B_W_FULL + HO_W_SLOTS, B_TM1_FULL = B_W_EMPTY + HO_W_SLOTS,
                 B_TM_EMPTY = B_TM1_FULL + 2, B_H_FULL = B_TM_EMPTY + 2, B_TM2_FULL = B_H_FULL + 1, B_COUNT = B_TM2_FULL + 1;
   static_assert(B_COUNT == HO_BARRIERS, "barrier map and shared-memory plan disagree");
   uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * B_COUNT);
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(HO_THREADS, 1) handoff_tc_kernel(const __grid_
   for (int i = threadIdx.x; i < HO_W2_BYTES / 16; i += HO_THREADS)      // the 1x1 weights stay resident
     reinterpret_cast<uint4*>(smem + p.off_w2)[i] = reinterpret_cast<const uint4*>(p.w + HO_W1_BYTES)[i];
   if (threadIdx.x == 0) {
-    mbar_init(BAR(B_WIN_FULL), 1); mbar_init(BAR(B_WIN_EMPTY), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_WIN_FULL + i), 1); mbar_init(BAR(B_WIN_EMPTY + i), 1); }
     // multicast: a slot is free when the issuers of BOTH CTAs are done with it (each commit arrives in both CTAs)
     for (int i = 0; i < HO_W_SLOTS; ++i) { mbar_init(BAR(B_W_FULL + i), 1); mbar_init(BAR(B_W_EMPTY + i), mc ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TM1_FULL + i), 1); mbar_init(BAR(B_TM_EMPTY + i), 4); }
@@ -144,11 +146,18 @@ __global__ void __launch_bounds__(HO_THREADS, 1) handoff_tc_kernel(const __grid_
       for (int it = 0; it < my_items; ++it) {
         const int item = min(raw_item(it), p.n_items - 1);
         const int64_t q0 = (int64_t)HO_GUARD + (int64_t)item * 128 - p.halo;
-        mbar_wait(BAR(B_WIN_EMPTY), (it & 1) ^ 1);
-        mbar_expect_tx(BAR(B_WIN_FULL), p.win_plane_bytes * (uint32_t)HO_PLANES);
-        for (int g = 0; g < HO_PLANES; ++g)
-          bulk_g2s(sbase + (uint32_t)g * p.win_plane_bytes, p.x + ((int64_t)g * p.plane_cells + q0) * 8, p.win_plane_bytes, BAR(B_WIN_FULL));
+        // the window in two K halves (channel-group planes 0..15 / 16..31): half 0 is free 32 MMAs before the tile
+        // ends, so the next tile's half 0 lands under them; half 1 follows behind the first weight chunks of the new
+        // tile and lands under its first 32 MMAs, which read half 0 only -- no window bubble between tiles
+        auto load_half = [&](int hf) {
+          mbar_wait(BAR(B_WIN_EMPTY + hf), (it & 1) ^ 1);
+          mbar_expect_tx(BAR(B_WIN_FULL + hf), p.win_plane_bytes * (uint32_t)(HO_PLANES / 2));
+          for (int g = hf * (HO_PLANES / 2); g < (hf + 1) * (HO_PLANES / 2); ++g)
+            bulk_g2s(sbase + (uint32_t)g * p.win_plane_bytes, p.x + ((int64_t)g * p.plane_cells + q0) * 8, p.win_plane_bytes, BAR(B_WIN_FULL + hf));
+        };
+        load_half(0);
         for (int c = 0; c < HO_CHUNKS; ++c) {
+          if (c == 8) load_half(1);
           mbar_wait(BAR(B_W_EMPTY + sl), sph ^ 1);
           mbar_expect_tx(BAR(B_W_FULL + sl), HO_CHUNK_BYTES);      // my half and the peer's half both land here
           const uint32_t dst = sbase + p.off_ring + (uint32_t)sl * HO_CHUNK_BYTES;
@@ -194,36 +203,39 @@ __global__ void __launch_bounds__(HO_THREADS, 1) handoff_tc_kernel(const __grid_
     const uint32_t a_kstep = 2u * win_plane16;
     uint32_t sl = 0, sph = 0, k = 0;
     for (int it = 0; it < my_items; ++it) {
-      mbar_wait_warp(BAR(B_WIN_FULL), (uint32_t)(it & 1));
       for (int par = 0; par < 4; ++par, ++k) {
         const uint32_t buf = k & 1u, use = k >> 1;
         if (k >= 2) mbar_wait_warp(BAR(B_TM_EMPTY + (int)buf), (use - 1u) & 1u);
         tc_fence_after();
         const int pa = par >> 1, pb = par & 1;
         const uint32_t d_acc = tmem_u + buf * 256u;
+        // K order of a parity: window half 0 (K-steps 0..7) for the four taps, then half 1 (weights packed alike)
 #pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
-          if (t == 2 && k > 0) gemm2(k - 1);                               // under this parity's MMAs
-          const uint32_t a_tap = a_base + (uint32_t)(ho_tap_offset(pa, t >> 1) * (int)pitch + ho_tap_offset(pb, t & 1));
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf == 1 && k > 0) gemm2(k - 1);                              // under this parity's MMAs
+          if (par == 0) mbar_wait_warp(BAR(B_WIN_FULL + hf), (uint32_t)(it & 1));
+#pragma unroll 1
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t a_tap = a_base + (uint32_t)(ho_tap_offset(pa, t >> 1) * (int)pitch + ho_tap_offset(pb, t & 1)) +
+                                   (uint32_t)hf * (uint32_t)(HO_KSTEPS / 2) * a_kstep;
 #pragma unroll
-          for (int c = 0; c < HO_KSTEPS / HO_CHUNK_KSTEPS; ++c) {
-            mbar_wait_warp(w_full0 + 8u * sl, sph);
-            tc_fence_after();
-            if (leader) {
-              const uint32_t b_c = ring16 + sl * (uint32_t)(HO_CHUNK_BYTES >> 4);
+            for (int c = 0; c < HO_KSTEPS / 2 / HO_CHUNK_KSTEPS; ++c) {
+              mbar_wait_warp(w_full0 + 8u * sl, sph);
+              tc_fence_after();
+              if (leader) {
+                const uint32_t b_c = ring16 + sl * (uint32_t)(HO_CHUNK_BYTES >> 4);
 #pragma unroll
-              for (int j = 0; j < HO_CHUNK_KSTEPS; ++j)
-                tc_mma_bf16(d_acc, desc_hi | (uint64_t)(a_tap + (uint32_t)(c * HO_CHUNK_KSTEPS + j) * a_kstep),
-                            desc_hi | (uint64_t)(b_c + (uint32_t)j * (uint32_t)(HO_KSTEP_BYTES >> 4)), ID256, (t | c | j) ? 1u : 0u);
-              if (mc) tc_commit_mc(w_empty0 + 8u * sl, 3); else tc_commit(w_empty0 + 8u * sl);
+                for (int j = 0; j < HO_CHUNK_KSTEPS; ++j)
+                  tc_mma_bf16(d_acc, desc_hi | (uint64_t)(a_tap + (uint32_t)(c * HO_CHUNK_KSTEPS + j) * a_kstep),
+                              desc_hi | (uint64_t)(b_c + (uint32_t)j * (uint32_t)(HO_KSTEP_BYTES >> 4)), ID256, (hf | t | c | j) ? 1u : 0u);
+                if (mc) tc_commit_mc(w_empty0 + 8u * sl, 3); else tc_commit(w_empty0 + 8u * sl);
+              }
+              if (++sl == (uint32_t)HO_W_SLOTS) { sl = 0; sph ^= 1u; }
             }
-            if (++sl == (uint32_t)HO_W_SLOTS) { sl = 0; sph ^= 1u; }
           }
+          if (par == 3 && leader) tc_commit(BAR(B_WIN_EMPTY + hf));          // this half of the window is done for the tile
         }
-        if (leader) {
-          if (par == 3) tc_commit(BAR(B_WIN_EMPTY));
-          tc_commit(BAR(B_TM1_FULL + (int)buf));
-        }
+        if (leader) tc_commit(BAR(B_TM1_FULL + (int)buf));
       }
     }
     if (k > 0) gemm2(k - 1);
@@ -326,22 +338,24 @@ extern "C" int sceneego_handoff_pack(const float* h_deconv_w, const float* h_gam
     h_b_out[co] = (float)((double)h_beta[co] - (double)h_mean[co] * scale[co]);
   }
   for (int o = 0; o < HO_OUT; ++o) h_b_out[HO_MID + o] = h_conv_b ? h_conv_b[o] : 0.f;
-  // GEMM 1 weights: [parity x tap x K-step][k-chunk 2][256 rows][8]
-  size_t chunk = 0;
+  // GEMM 1 weights in the order the kernel consumes them: [parity][window half][tap][K-step of the half][k-chunk 2][256 rows][8]
+  size_t kstep_slot = 0;
   for (int par = 0; par < 4; ++par)
-    for (int t = 0; t < 4; ++t) {
-      const int ky = ho_tap_k(par >> 1, t >> 1), kx = ho_tap_k(par & 1, t & 1);
-      for (int ks = 0; ks < HO_KSTEPS; ++ks, ++chunk) {
-        uint16_t* dst = h_w_out + chunk * (HO_KSTEP_BYTES / 2);
-        for (int c = 0; c < 2; ++c)
-          for (int co = 0; co < HO_MID; ++co)
-            for (int e = 0; e < 8; ++e) {
-              const int ci = ks * 16 + c * 8 + e;
-              dst[((size_t)c * HO_MID + co) * 8 + e] =
-                  f2bf((float)((double)h_deconv_w[(((size_t)ci * HO_MID + co) * 4 + ky) * 4 + kx] * scale[co]));
-            }
+    for (int hf = 0; hf < 2; ++hf)
+      for (int t = 0; t < 4; ++t) {
+        const int ky = ho_tap_k(par >> 1, t >> 1), kx = ho_tap_k(par & 1, t & 1);
+        for (int kh = 0; kh < HO_KSTEPS / 2; ++kh, ++kstep_slot) {
+          const int ks = hf * (HO_KSTEPS / 2) + kh;
+          uint16_t* dst = h_w_out + kstep_slot * (HO_KSTEP_BYTES / 2);
+          for (int c = 0; c < 2; ++c)
+            for (int co = 0; co < HO_MID; ++co)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = ks * 16 + c * 8 + e;
+                dst[((size_t)c * HO_MID + co) * 8 + e] =
+                    f2bf((float)((double)h_deconv_w[(((size_t)ci * HO_MID + co) * 4 + ky) * 4 + kx] * scale[co]));
+              }
+        }
       }
-    }
   uint16_t* w2 = h_w_out + HO_W1_BYTES / 2;                  // Conv2d weight (32, 256): [K-step][k-chunk][32 rows][8]
   for (int ks = 0; ks < HO_MID / 16; ++ks)
     for (int c = 0; c < 2; ++c)
