@@ -26,6 +26,11 @@ __device__ __forceinline__ uint32_t act_pack2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t act_pack2_relu(float lo, float hi) {      // max(x, 0) and the rounding in one F2FP
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ float2 act_unpack2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 __device__ __forceinline__ __nv_bfloat16 act_from_float(float v) {
   const uint32_t r = act_pack2(v, 0.f);
@@ -40,6 +45,11 @@ constexpr uint32_t kIdescAB = (1u << 7) | (1u << 10);      // instruction descri
 __device__ __forceinline__ uint32_t act_pack2(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t act_pack2_relu(float lo, float hi) {      // max(x, 0) and the rounding in one F2FP
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ float2 act_unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 __device__ __forceinline__ __nv_bfloat16 act_from_float(float v) { return __float2bfloat16(v); }

@@ -142,49 +142,69 @@ __global__ void __launch_bounds__(256, 2) tail_mlp_kernel(const __grid_constant_
 // SM at 128 registers; rolling prefetch, more occupancy and cross-tile interleaving all made it slower), so the
 // chain of three GEMMs moves to the 5th-generation tensor cores with the intermediates staying on the SM:
 //   one CTA per SM = 8 independent groups of 4 warps; a group walks its own 128-position tiles:
-//     TMA (4 planes x 128 cells x 16 B, double-buffered)            -> A tile in shared memory
-//     tcgen05.mma M=128 N=32 K=32 (W1 resident in smem)             -> 32 TMEM columns
-//     tcgen05.ld, + bias, ReLU, bf16 (the unfused chain's rounding) -> the SAME smem tile, now layer 2's A operand
-//     tcgen05.mma N=32 (W2) -> ld / bias / ReLU / bf16 -> smem -> tcgen05.mma N=16 (W3) -> ld, + bias -> f32 logits
+//     TMA (4 planes x 128 cells x 16 B, double-buffered)              -> A tile in shared memory
+//     tcgen05.mma M=128 N=32 (W1 resident in smem)                    -> 32 TMEM columns
+//     tcgen05.ld, ReLU + bf16 in one F2FP (the unfused chain's rounding), tcgen05.st -> 16 TMEM columns = layer 2's A operand
+//     tcgen05.mma N=32 (W2, A from tensor memory) -> ld / pack / st -> tcgen05.mma N=16 (W3, A from tensor memory) -> ld -> f32 logits
+//   The biases ride in the MMAs: every layer starts with a K=16 MMA of a constant "ones" tile against a B block whose
+//   first two K rows hold the bias split in two 16-bit parts (hi + lo: exact to 2^-17 of the bias), so the epilogues
+//   have no adds and no shared-memory bias reads.  Round-2 form: with the hidden activations going through shared
+//   memory (four 16-byte stores per row and layer + a proxy fence) and the bias added in the epilogue the kernel was
+//   bound by instruction issue (~330 instructions per voxel, ncu: issue active 69 %, DRAM 47 %).
 //   The 4 warps of a group are the four TMEM lane quarters; its first lane issues the TMA and the MMAs, a named
-//   barrier per group orders "tile written" before "MMA issued".  Eight groups keep eight such dependent chains
-//   (~2000 cycles each) in flight per SM, which is what hides their latency.
+//   barrier per group orders "hidden tile written" before "MMA issued".  Eight groups keep eight such dependent chains
+//   in flight per SM, which is what hides their latency.
 // ---------------------------------------------------------------------------
 constexpr int TT_GROUPS = 8;
 constexpr int TT_THREADS = TT_GROUPS * 128;
 constexpr uint32_t TT_TILE_BYTES = 4u * 128u * 16u;          // 4 channel-group planes x 128 rows x 16 B
+// shared-memory layout: [W1 2048][W2 2048][W3 1024][bias blocks 1024 + 1024 + 512][ones tile 4096][barriers 256][tmem ptr 128]
+//                       then 8 groups x 2 buffers x 8 KB tiles (128-byte aligned)
+constexpr uint32_t TT_OFF_W1 = 0, TT_OFF_W2 = 2048, TT_OFF_W3 = 4096, TT_OFF_BB = 5120, TT_OFF_ONES = 7680, TT_OFF_BAR = 11776,
+                   TT_OFF_TMEM = 12032, TT_OFF_TILES = 12160;
+constexpr uint32_t TT_GROUP_COLS = 64;                        // per group: 32 accumulator columns + 16 hidden (packed) columns
 
 __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_constant__ TailParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [W1 2048][W2 2048][W3 1024][bias 80 f32 -> 384][barriers 8 groups x 3 x 8 B -> 256][tmem ptr 16]
-  //         then 8 groups x 2 buffers x 8 KB tiles (128-byte aligned)
-  constexpr uint32_t OFF_W1 = 0, OFF_W2 = 2048, OFF_W3 = 4096, OFF_BIAS = 5120, OFF_BAR = 5504, OFF_TMEM = 5760,
-                     OFF_TILES = 5888;
   const uint32_t sbase = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int grp = warp >> 2, quarter = warp & 3;
-  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TT_OFF_TMEM);
   for (int i = threadIdx.x; i < 5120 / 16; i += TT_THREADS)
     reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(p.w1)[i];      // w1 | w2 | w3 are contiguous in the blob
-  if (threadIdx.x < 80) s_bias[threadIdx.x] = threadIdx.x < 32 ? p.b1[threadIdx.x] : threadIdx.x < 64 ? p.b2[threadIdx.x - 32] : p.b3[threadIdx.x - 64];
-  auto BAR = [&](int g, int i) { return sbase + OFF_BAR + 8u * (uint32_t)(g * 3 + i); };   // 0,1: TMA full[buf]; 2: MMA done
+  // bias blocks, one per layer, in the weights' [k-chunk 2][n rows][8] form: K rows 0 and 1 = bias hi / lo, the rest 0
+  for (int i = threadIdx.x; i < (1024 + 1024 + 512) / 16; i += TT_THREADS) {
+    const int layer = i < 64 ? 0 : i < 128 ? 1 : 2;
+    const int n = layer == 2 ? 16 : 32;
+    const int cell = i - (layer == 0 ? 0 : layer == 1 ? 64 : 128);                    // [k-chunk][row]
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (cell < n) {
+      const float bv = layer == 0 ? p.b1[cell] : layer == 1 ? p.b2[cell] : p.b3[cell];
+      const float hi = act_to_float(act_from_float(bv));
+      v.x = act_pack2(hi, bv - hi);
+    }
+    reinterpret_cast<uint4*>(smem + TT_OFF_BB)[i] = v;
+  }
+  // the constant A tile of the bias MMAs: K elements 0 and 1 of every row are 1, the other 14 are 0
+  for (int i = threadIdx.x; i < 4096 / 16; i += TT_THREADS)
+    reinterpret_cast<uint4*>(smem + TT_OFF_ONES)[i] = i < 128 ? make_uint4(act_pack2(1.f, 1.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
+  auto BAR = [&](int g, int i) { return sbase + TT_OFF_BAR + 8u * (uint32_t)(g * 3 + i); };   // 0,1: TMA full[buf]; 2: MMA done
   if (threadIdx.x == 0) {
     for (int g = 0; g < TT_GROUPS; ++g) { mbar_init(BAR(g, 0), 1); mbar_init(BAR(g, 1), 1); mbar_init(BAR(g, 2), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the weights were written with generic stores
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // weights, bias blocks, ones tile: generic stores
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *s_tmem + (uint32_t)grp * 32u;               // this group's 32 accumulator columns
+  const uint32_t tmem = *s_tmem + (uint32_t)grp * TT_GROUP_COLS;     // this group's accumulator columns; hidden tile at +32
   const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
-  const uint32_t tile0 = sbase + OFF_TILES + (uint32_t)grp * 2u * TT_TILE_BYTES;
+  const uint32_t tile0 = sbase + TT_OFF_TILES + (uint32_t)grp * 2u * TT_TILE_BYTES;
   const bool issuer = (warp & 3) == 0 && lane == 0;
   const int S = p.ls.side;
   const size_t N3 = (size_t)S * S * S;
@@ -197,6 +217,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_con
   constexpr uint32_t idesc0 = (1u << 4) | kIdescAB | (8u << 24);
   constexpr uint32_t ID32 = idesc0 | ((32u >> 3) << 17), ID16 = idesc0 | ((16u >> 3) << 17);
   const uint32_t a_lbo = (2048u >> 4) << 16;
+  const uint32_t ones = (((sbase + TT_OFF_ONES) >> 4) & 0x3FFFu) | a_lbo;
   auto load_tile = [&](int64_t t, int buf) {                       // issuer only
     const uint32_t dst = tile0 + (uint32_t)buf * TT_TILE_BYTES;
     mbar_expect_tx(BAR(grp, buf), TT_TILE_BYTES);
@@ -205,32 +226,36 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_con
     for (int g = 0; g < 4; ++g)
       bulk_g2s(dst + (uint32_t)g * 2048u, p.src + ((int64_t)g * p.ls.plane_stride + q0) * 8, 2048u, BAR(grp, buf));
   };
-  // one layer: A = the group's tile, B = weights at `w_off` with `n` rows; result in the group's TMEM columns
-  auto gemm = [&](uint32_t a_tile, uint32_t w_off, uint32_t n, uint32_t idesc) {   // issuer only
-    const uint32_t a = ((a_tile >> 4) & 0x3FFFu) | a_lbo;
-    const uint32_t b = (((sbase + w_off) >> 4) & 0x3FFFu) | (n << 16);               // LBO = n rows x 16 B
-    tc_mma_bf16(tmem, DESC(a), DESC(b), idesc, 0u);
-    tc_mma_bf16(tmem, DESC(a + (4096u >> 4)), DESC(b + 2u * n), idesc, 1u);          // channels 16..31
+  auto bdesc = [&](uint32_t off, uint32_t n) { return (((sbase + off) >> 4) & 0x3FFFu) | (n << 16); };   // LBO = n rows x 16 B
+  // one layer (issuer only): bias, then the two K-steps of the data; A from the shared-memory tile (layer 1) or from
+  // the group's packed hidden columns in tensor memory (layers 2, 3)
+  auto gemm = [&](bool a_in_smem, uint32_t a_tile, uint32_t w_off, uint32_t bb_off, uint32_t n, uint32_t idesc) {
+    tc_mma_bf16(tmem, DESC(ones), DESC(bdesc(bb_off, n)), idesc, 0u);
+    const uint32_t b = bdesc(w_off, n);
+    if (a_in_smem) {
+      const uint32_t a = ((a_tile >> 4) & 0x3FFFu) | a_lbo;
+      tc_mma_bf16(tmem, DESC(a), DESC(b), idesc, 1u);
+      tc_mma_bf16(tmem, DESC(a + (4096u >> 4)), DESC(b + 2u * n), idesc, 1u);        // channels 16..31
+    } else {
+      tc_mma_bf16_ts(tmem, tmem + 32u, DESC(b), idesc, 1u);
+      tc_mma_bf16_ts(tmem, tmem + 40u, DESC(b + 2u * n), idesc, 1u);
+    }
     tc_commit(BAR(grp, 2));
   };
   const uint32_t bar_id = 1u + (uint32_t)grp;                        // named barrier of this group (0 = __syncthreads)
   auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
-  // bias + ReLU + bf16 of this row's 32 accumulators -> the row's four 16-byte cells of the tile
-  auto hidden_to_tile = [&](uint32_t a_tile, const float* bias) {
+  // ReLU + 16-bit rounding of this row's 32 accumulators -> the row's 16 packed columns of the hidden tile
+  auto hidden_to_tmem = [&]() {
     uint32_t raw[2][16];
     tc_ld16(taddr, raw[0]);
     tc_ld16(taddr + 16u, raw[1]);
     tc_wait_ld();
-    const uint32_t row = a_tile + (uint32_t)(quarter * 32 + lane) * 16u;
+    uint32_t pk[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(raw[g >> 1][(g & 1) * 8 + j]) + bias[8 * g + j], 0.f);
-      const uint4 v = pack8(o);
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + (uint32_t)g * 2048u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
+    for (int j = 0; j < 16; ++j)
+      pk[j] = act_pack2_relu(__uint_as_float(raw[j >> 3][2 * (j & 7)]), __uint_as_float(raw[j >> 3][2 * (j & 7) + 1]));
+    tc_st16(taddr + 32u, pk);
+    tc_wait_st();
     tc_fence_before();
   };
   if (issuer && tile < n_tiles) load_tile(tile, 0);
@@ -242,22 +267,22 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_con
     if (issuer) {
       mbar_wait(BAR(grp, buf), ph_full[buf]);
       tc_fence_after();
-      gemm(a_tile, OFF_W1, 32u, ID32);
+      gemm(true, a_tile, TT_OFF_W1, TT_OFF_BB, 32u, ID32);
       if (tile + stride < n_tiles) load_tile(tile + stride, buf ^ 1);   // that buffer's last reader (an MMA) was awaited
     }
     ph_full[buf] ^= 1u;
     mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
     tc_fence_after();
-    hidden_to_tile(a_tile, s_bias);
+    hidden_to_tmem();
     group_sync();
     // ---- layer 2
-    if (issuer) { tc_fence_after(); gemm(a_tile, OFF_W2, 32u, ID32); }
+    if (issuer) { tc_fence_after(); gemm(false, 0u, TT_OFF_W2, TT_OFF_BB + 1024u, 32u, ID32); }
     mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
     tc_fence_after();
-    hidden_to_tile(a_tile, s_bias + 32);
+    hidden_to_tmem();
     group_sync();
     // ---- layer 3 (16 columns, cout_real of them real)
-    if (issuer) { tc_fence_after(); gemm(a_tile, OFF_W3, 16u, ID16); }
+    if (issuer) { tc_fence_after(); gemm(false, 0u, TT_OFF_W3, TT_OFF_BB + 2048u, 16u, ID16); }
     mbar_wait(BAR(grp, 2), ph_mma); ph_mma ^= 1u;
     tc_fence_after();
     uint32_t raw[16];
@@ -277,13 +302,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tail_tc_kernel(const __grid_con
         float* o = p.dst + (size_t)b * p.cout_real * N3 + ((size_t)x * S + y) * S + z;
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          if (c < p.cout_real) __stcs(o + (size_t)c * N3, __uint_as_float(raw[c]) + s_bias[64 + c]);
+          if (c < p.cout_real) __stcs(o + (size_t)c * N3, __uint_as_float(raw[c]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"(256u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"(512u) : "memory");
 }
 
 // CUDA-core checker (op.impl = 1): one thread per voxel, same packed weights, same bf16 roundings.
@@ -361,7 +386,7 @@ int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const v
   }
   SE_REQUIRE((const char*)p.w2 == (const char*)p.w1 + 2048 && (const char*)p.w3 == (const char*)p.w1 + 4096 &&
                  ((uintptr_t)p.w1 & 15) == 0, "v2v_run: op %d: tail weights must be one aligned 5 KB segment", op_index);
-  const size_t smem_bytes = 5888 + (size_t)TT_GROUPS * 2 * TT_TILE_BYTES;
+  const size_t smem_bytes = TT_OFF_TILES + (size_t)TT_GROUPS * 2 * TT_TILE_BYTES;
   if (int rc = ensure_max_dynamic_smem((const void*)tail_tc_kernel, (int)smem_bytes)) return rc;
   const int64_t n_tiles = (p.n_pos + 127) / 128;
   int64_t blocks = (n_tiles + TT_GROUPS - 1) / TT_GROUPS;
