@@ -565,11 +565,23 @@ def stage_kernel_timings(net, feat_d, depth_d, B, args, V, hbm_peak, tc_peak):
     rec("feature_conv1x1", ms, 256 * 64 * 64 * 4 + 64 * 64 * 32 * 4, "read (256,64,64) f32 + write (64,64,32) f32")
     ms = timed(lambda: _lib.unproject(feat32, grid, None, V, 2.0, 1024, 1280, None, in_buf, pg.lay_in,
                                       extra_zero_planes=pg.extra_zero_planes))
-    rec("unproject", ms, 64 * 64 * 32 * 4 + N * 32 * 2 + N * 2 + N * 8,
-        "read 0.524 MB features + the grid table, write 32 bf16 channels + the cleared occupancy plane")
+    rec("unproject", ms, 64 * 64 * 32 * 4 + N * 32 * 2 + N * 16 * pg.extra_zero_planes + N * 8,
+        "read 0.524 MB features + the grid table, write 32 bf16 channels" +
+        (" + the cleared occupancy plane" if pg.extra_zero_planes else ""))
     d = depth_d[:n]
-    ms = timed(lambda: _lib.voxelize_depth(d, net._ray_dev, 1024, 1280, V, 2.0, None, in_buf, pg.lay_in, channel=32))
-    rec("voxelize", ms, 1024 * 1280 * 4, "read (1024,1280) f32 depth; ray table (31.5 MB) shared by all frames; sparse bf16 scatter")
+    if pg.zwin:
+        # lift()'s path for the marching stem: one store per pixel into the program's plain f32 grid, then one pass
+        # that builds the whole z-window occupancy plane from it and re-zeroes the grid
+        scratch = pg.occ_scratch[:n]
+        ms = timed(lambda: _lib.voxelize_depth(d, net._ray_dev, 1024, 1280, V, 2.0, scratch, None, pg.lay_in, channel=32))
+        rec("voxelize", ms, 1024 * 1280 * 4,
+            "read (1024,1280) f32 depth; ray table (31.5 MB) shared by all frames; sparse f32 scatter; bound by fp64 instruction issue, not HBM")
+        ms = timed(lambda: _lib.occ_expand_zwin(scratch, in_buf, pg.lay_in, 32))
+        rec("occ_expand_zwin", ms, N * 4 + N * 16, "read the (V,V,V) f32 grid, write the z-window occupancy plane (16 B per voxel)")
+    else:
+        ms = timed(lambda: _lib.voxelize_depth(d, net._ray_dev, 1024, 1280, V, 2.0, None, in_buf, pg.lay_in, channel=32))
+        rec("voxelize", ms, 1024 * 1280 * 4,
+            "read (1024,1280) f32 depth; ray table (31.5 MB) shared by all frames; sparse bf16 scatter")
     vn.profile_chunk(pg, n, logits)     # warm-up
     prof = vn.profile_chunk(pg, n, logits)
     conv_ms = sum(ms for m, ms in prof if m["kind"] == "conv")

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCENEEGO_ABI_VERSION 4
+#define SCENEEGO_ABI_VERSION 5
 
 enum {
   SCENEEGO_OK = 0,
@@ -188,6 +188,13 @@ int sceneego_voxelize_depth_dataset_f64(const float* d_depth_raw, int batch, int
  * In place on a plain planar bf16 volume whose channels [0,c) hold the lifted features and channel 2c the
  * occupancy: writes channels [c,2c) = features * occupancy at every voxel. */
 int sceneego_intersect_bf16(void* d_vol, const sceneego_vol_layout_t* lay, int batch, int c, void* stream);
+
+/* Same call site (the scene channel of voxel_net_depth.py:251-262) for the marching stem's z-window layout: build the
+ * occupancy plane of `channel` from a plain (B,V,V,V) f32 occupancy grid written by sceneego_voxelize_depth*_f64 with
+ * d_occ_f32 -- cell (x,y,z) = occ[x][y][z-3..z+4] -- writing EVERY real cell (no clearing needed beforehand) and
+ * leaving the grid all-zero again for the next batch (it must be zero before the first voxelisation). */
+int sceneego_occ_expand_zwin_bf16(float* d_occ_f32, void* d_vol, const sceneego_vol_layout_t* lay, int batch, int channel,
+                                  void* stream);
 
 /* Conversions between (B,C,S,S,S) f32 NCDHW and planar padded bf16 (for the
  * scene_volumes= input path, voxel_net_depth.py:246-249, and for tests). */

@@ -46,7 +46,7 @@ SYMBOLS = [
     "sceneego_v2v_last_launch_count", "sceneego_softargmax_workspace_bytes", "sceneego_softargmax3d_f32",
     "sceneego_world2camera_f32", "sceneego_grid_sample_f32", "sceneego_vol_layout_make_s2d",
     "sceneego_v2v_stem_s2d_weight_bytes", "sceneego_v2v_pack_stem_s2d", "sceneego_v2v_pack_conv_march", "sceneego_voxelize_depth_raw_f64", "sceneego_intersect_bf16", "sceneego_pose_errors_f64",
-    "sceneego_voxelize_depth_dataset_f64", "sceneego_vol_layout_make_zwin", "sceneego_v2v_stem_march_weight_bytes",
+    "sceneego_voxelize_depth_dataset_f64", "sceneego_vol_layout_make_zwin", "sceneego_occ_expand_zwin_bf16", "sceneego_v2v_stem_march_weight_bytes",
     "sceneego_v2v_pack_stem_march", "sceneego_handoff_weight_bytes", "sceneego_handoff_workspace_bytes", "sceneego_handoff_pack",
     "sceneego_backbone_handoff_f32",
 ]
@@ -101,7 +101,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sceneego_handoff_workspace_bytes.restype = C.c_size_t
     lib.sceneego_v2v_stem_s2d_weight_bytes.restype = C.c_size_t
     lib.sceneego_softargmax_workspace_bytes.restype = C.c_size_t
-    if lib.sceneego_abi_version() != 4:
+    if lib.sceneego_abi_version() != 5:
         raise SceneEgoError("libsceneego_b200.so ABI version mismatch")
     if path is None and lib.sceneego_act_dtype() != (1 if _ACT == "f16" else 0):
         raise SceneEgoError(f"{p} was not compiled for {_ACT} activations")
@@ -319,6 +319,15 @@ def voxelize_depth_dataset(depth_raw: torch.Tensor, pre_hw, clamp_max: float, ra
         raise SceneEgoError("voxelize_depth_dataset: the ray table must be (pre_h, pre_w, 3)")
     _call("sceneego_voxelize_depth_dataset_f64", depth_raw, depth_raw, b, h, w, int(pre_hw[0]), int(pre_hw[1]),
           C.c_float(clamp_max), ray, int(volume_size), C.c_double(cuboid_side), occ_f32)
+
+
+def occ_expand_zwin(occ_f32: torch.Tensor, vol: torch.Tensor, lay: VolLayout, channel: int) -> None:
+    """Plain (B,V,V,V) f32 occupancy grid -> the z-window occupancy plane of `channel` in the marching stem's input
+    (every real cell written); the grid is left all-zero for the next batch."""
+    b = occ_f32.shape[0]
+    if occ_f32.dtype != torch.float32 or not occ_f32.is_contiguous() or tuple(occ_f32.shape[1:]) != (lay.side,) * 3:
+        raise SceneEgoError("occ_expand_zwin: needs a contiguous (B,V,V,V) f32 grid")
+    _call("sceneego_occ_expand_zwin_bf16", occ_f32, occ_f32, vol, C.byref(lay), int(b), int(channel))
 
 
 def intersect(vol_bf16: torch.Tensor, lay: VolLayout, batch: int, channels: int) -> None:

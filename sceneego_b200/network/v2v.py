@@ -109,8 +109,13 @@ class _Program:
         self.zwin = special and stem == "march"
         self.lay_in = (_lib.vol_layout_s2d(side, chunk) if self.s2d else _lib.vol_layout_zwin(side, chunk) if self.zwin
                        else _lib.vol_layout(side, 3, chunk))
-        # zero planes the unprojection kernel clears behind the 32 feature channels (the occupancy plane(s))
-        self.extra_zero_planes = 1 if self.zwin else (self.in_pad - 32) // 8
+        # zero planes the unprojection kernel clears behind the 32 feature channels (the occupancy plane(s)); none for
+        # the z-window layout: its occupancy plane is written whole, from `occ_scratch` (a plain f32 grid the
+        # voxelisation scatters into with one store per pixel; _lib.occ_expand_zwin leaves it all-zero again) or by
+        # pack_volume (the scene_volumes= path)
+        self.extra_zero_planes = 0 if self.zwin else (self.in_pad - 32) // 8
+        self.occ_scratch = (torch.zeros(chunk, side, side, side, dtype=torch.float32, device=device)
+                            if self.zwin and torch.device(device).type == "cuda" else None)
         self.lays = [_lib.vol_layout(side >> l, 1, chunk) for l in range(6)]
         self.level_channels = EncoderDecorder.CHANNELS
         self.in_buf = self._new_buffer(-1)

@@ -381,14 +381,21 @@ class VoxelNetwork_depth(nn.Module):
             else:
                 d = depth_map_batch
                 d = d.reshape(n, d.shape[-2], d.shape[-1]).contiguous().float()
+                # z-window input (the marching stem): one store per pixel into the program's plain f32 grid, then
+                # one pass builds the whole occupancy plane from it and leaves the grid zero for the next batch
+                scratch = pg.occ_scratch[:n] if pg.zwin else None
+                dst_bf16 = None if pg.zwin else in_buf
                 if self.depth_preprocess is not None:
                     ph, pw, cm = self.depth_preprocess
                     _lib.voxelize_depth_raw(d, (ph, pw), float(cm), self._ray_dev, self.image_height,
-                                            self.image_width, v, float(self.cuboid_side), None, in_buf, pg.lay_in,
+                                            self.image_width, v, float(self.cuboid_side), scratch, dst_bf16, pg.lay_in,
                                             channel=scene_ch)
                 else:
                     _lib.voxelize_depth(d, self._ray_dev, self.image_height, self.image_width, v,
-                                        float(self.cuboid_side), None, in_buf, pg.lay_in, channel=scene_ch)
+                                        float(self.cuboid_side), scratch, dst_bf16, pg.lay_in, channel=scene_ch)
+                if pg.zwin:
+                    _lib.occ_expand_zwin(scratch, in_buf, pg.lay_in, scene_ch)
+                    launches += 1
                 if self.with_intersection:
                     _lib.intersect(in_buf, pg.lay_in, n, 32)
                     launches += 1

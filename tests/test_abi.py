@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list out of sync with the header"
     hdr = open(os.path.join(util.ROOT, "include", "sceneego_b200.h")).read()
-    assert lib.sceneego_abi_version() == int(re.search(r"#define SCENEEGO_ABI_VERSION (\d+)", hdr).group(1)) == 4
+    assert lib.sceneego_abi_version() == int(re.search(r"#define SCENEEGO_ABI_VERSION (\d+)", hdr).group(1)) == 5
 
 
 def test_struct_layouts_match_header():

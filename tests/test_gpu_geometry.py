@@ -79,6 +79,17 @@ def _voxelize(cam, depth, V, side=2.0):
     ref3 = _lib.alloc_volume(lay3, 40, "cuda")
     _lib.pack_volume(occ.unsqueeze(1).contiguous(), ref3, lay3, c_offset=32)      # gather form of the same plane
     assert torch.equal(buf3[4], ref3[4]), "scattered z-window cells differ from the packed ones"
+    # the path lift() takes: one store per pixel into a plain f32 grid, then the whole plane from that grid in one
+    # pass that also leaves the grid all-zero for the next batch
+    scratch = occ.clone()
+    buf4 = _lib.alloc_volume(lay3, 40, "cuda")
+    buf4[4].fill_(7.0)                                             # stale cells must all be overwritten
+    _lib.occ_expand_zwin(scratch, buf4, lay3, 32)
+    written = buf4[4] != 7.0                                       # all eight entries of every real cell, nothing else
+    assert int(written.sum().item()) == d.shape[0] * V ** 3 * 8, "expand: not exactly the real cells were written"
+    assert torch.equal(buf4[4][written], buf3[4][written]), "expanded z-window cells differ from the scattered ones"
+    assert scratch.abs().max().item() == 0.0, "expand: the grid is not all-zero afterwards"
+    assert buf4[:4].abs().max().item() == 0.0, "expand touched a feature plane"
     return occ.cpu().numpy()
 
 

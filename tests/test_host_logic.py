@@ -39,7 +39,8 @@ def test_program_structure_and_flops():
     assert pg.flops * 8 == m.flops_per_frame(64)
     assert pg.ops[0].ksize == 7 and pg.ops[0].cin == 33 and pg.ops[0].cout == 16
     assert pg.ops[0].lay_src.zwin == 1 and pg.ops[0].lay_src.s2d == 0 and pg.ops[0].lay_src.side == 32 and pg.ops[0].lay_src.pad == 3
-    assert pg.extra_zero_planes == 1 and pg.buffers[pg.in_buf].shape[0] == 5          # 4 feature planes + z-window occupancy
+    # 4 feature planes + the z-window occupancy plane, which is written whole from the program's plain f32 grid
+    assert pg.extra_zero_planes == 0 and pg.buffers[pg.in_buf].shape[0] == 5
     m2 = V2VModel(33, 15)
     m2.stem = "s2d"                                                                    # the round-1 stem stays selectable
     pg2 = m2.program(32, 2, torch.device("cpu"))
