@@ -21,7 +21,7 @@ LIB = os.path.join(HERE, "libsceneego_b200.so")            # bf16 activations / 
 LIB_F16 = os.path.join(HERE, "libsceneego_b200_f16.so")    # the same sources with -DSCENEEGO_ACT_F16 (fp16 storage)
 HASH_FILE = LIB + ".srchash"
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "stem_march.cu", "tail.cu", "march.cu", "eval.cu", "handoff.cu"]
+SOURCES = ["geometry.cu", "softargmax.cu", "v2v.cu", "stem.cu", "stem_march.cu", "tail.cu", "march.cu", "eval.cu", "handoff.cu", "feature_conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -128,6 +128,8 @@ constexpr int kNumSMs = 148;
 
 int launch_stem_s2d(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
                     bool simt, cudaStream_t st);
+int launch_feature_conv1x1_simt(const float* d_feat, const float* d_weight, const float* d_bias, float* d_out, int batch,
+                                int cin, int cout, int h, int w, cudaStream_t st);
 int launch_stem_march(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,
                       bool simt, cudaStream_t st);
 int launch_tail_mlp(const sceneego_v2v_op_t& op, void* const* d_buffers, const void* d_blob, int batch, int op_index,

@@ -645,15 +645,17 @@ extern "C" int sceneego_project_voxels_f32(const sceneego_calib_t* calib, int V,
   return SCENEEGO_OK;
 }
 
-extern "C" int sceneego_feature_conv1x1_f32(const float* d_feat, const float* d_weight, const float* d_bias,
-                                            float* d_out, int batch, int cin, int cout, int h, int w, void* stream) {
-  SE_REQUIRE(d_feat && d_weight && d_bias && d_out, "feature_conv1x1: null argument");
+// the CUDA-core form (any cin that is a multiple of 32; csrc/feature_conv.cu holds the entry point and the tensor-core form)
+namespace sceneego {
+int launch_feature_conv1x1_simt(const float* d_feat, const float* d_weight, const float* d_bias, float* d_out, int batch,
+                                int cin, int cout, int h, int w, cudaStream_t st) {
   SE_REQUIRE(cout == FC_CO && cin % FC_KC == 0 && batch > 0, "feature_conv1x1: need cout == 32, cin %% 32 == 0");
   dim3 grid((h * w + FC_PIX - 1) / FC_PIX, batch);
-  feature_conv1x1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feat, d_weight, d_bias, d_out, cin, h * w);
+  feature_conv1x1_kernel<<<grid, 256, 0, st>>>(d_feat, d_weight, d_bias, d_out, cin, h * w);
   SE_CUDA_LAUNCH_CHECK("feature_conv1x1");
   return SCENEEGO_OK;
 }
+}  // namespace sceneego
 
 extern "C" int sceneego_features_upsample_pad_f32(const float* d_in, float* d_out, int batch, int c, int h, int w,
                                                   int up, int pad, void* stream) {

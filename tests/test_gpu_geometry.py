@@ -275,6 +275,32 @@ def test_unproject_vs_reference_golden(cam, tables64):
         assert torch.equal(zw[:, :32], planar[:, :32]) and zw[:, 32].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("B,h,w", [(2, 64, 64), (3, 20, 27), (1, 8, 8)])
+def test_feature_conv1x1_tensor_core_split_vs_fp64(B, h, w):
+    """process_features[0] (Conv2d(256,32,1), network/voxel_net_depth.py:58-63) on tcgen05 with operands split into two
+    bf16 parts (three MMAs per product): fp32-grade accuracy -- within 2e-5 of the output range of an fp64 evaluation,
+    where the plain fp32 CUDA-core kernel (SCENEEGO_FEATURE_CONV_SIMT=1) sits at ~1e-6 -- incl. a ragged last tile."""
+    import os
+    from sceneego_b200 import _lib
+    g = torch.Generator().manual_seed(B * 100 + h)
+    x = (torch.randn(B, 256, h, w, generator=g).abs() * 3.0).cuda()
+    wt = (torch.randn(32, 256, 1, 1, generator=g) * 0.08).cuda()
+    bs = (torch.randn(32, generator=g) * 0.1).cuda()
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), bs.double()).permute(0, 2, 3, 1)
+    rng = (ref.max() - ref.min()).item()
+    got = _lib.feature_conv1x1(x, wt, bs)
+    os.environ["SCENEEGO_FEATURE_CONV_SIMT"] = "1"
+    try:
+        simt = _lib.feature_conv1x1(x, wt, bs)
+    finally:
+        del os.environ["SCENEEGO_FEATURE_CONV_SIMT"]
+    e_tc = (got.double() - ref).abs().max().item() / rng
+    e_simt = (simt.double() - ref).abs().max().item() / rng
+    print(f"feature_conv1x1 B={B} {h}x{w}: max-abs/range vs fp64: tensor-core split {e_tc:.2e}, fp32 CUDA-core {e_simt:.2e}")
+    assert got.shape == (B, h, w, 32) and e_tc <= 2e-5 and e_simt <= 5e-6
+    assert torch.equal(_lib.feature_conv1x1(x, wt, bs), got)            # deterministic
+
+
 def test_materialised_features_and_generic_grid_sample(tables64):
     """Output #2 of the reference forward and the op-level drop-in: gathering from the
     materialised 1024x1280 map with the generic kernel equals the fused gather (loop == batch)."""
