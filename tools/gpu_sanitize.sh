@@ -11,3 +11,10 @@ tail -6 gpurun_out/r02_sanitize_handoff.log
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --launch-timeout 120 \
   python -m pytest tests/test_gpu_geometry.py -q -x -k "dataset or demo_frames" > gpurun_out/r02_sanitize_geometry.log 2>&1; echo "rc=$?" >> gpurun_out/r02_sanitize_geometry.log
 tail -6 gpurun_out/r02_sanitize_geometry.log
+# final round-2 kernels: fused tail with the hidden tile in tensor memory, split-operand feature conv, z-window expand (inside the demo-frame tests above)
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --launch-timeout 120 \
+  python -m pytest tests/test_gpu_v2v.py -q -x -k "tail" > gpurun_out/r02_sanitize_tail.log 2>&1; echo "rc=$?" >> gpurun_out/r02_sanitize_tail.log
+tail -4 gpurun_out/r02_sanitize_tail.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --launch-timeout 120 \
+  python -m pytest tests/test_gpu_geometry.py -q -x -k "feature_conv" > gpurun_out/r02_sanitize_fc.log 2>&1; echo "rc=$?" >> gpurun_out/r02_sanitize_fc.log
+tail -4 gpurun_out/r02_sanitize_fc.log
