@@ -315,15 +315,19 @@ __global__ void __launch_bounds__(128) unproject_kernel(const float* __restrict_
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     if (cell[t] >= 0) {
-      const float4* src = reinterpret_cast<const float4*>(fb + (size_t)cell[t] * C);
+      // 256-bit loads (sm_100): a warp's lanes fall into ~6 distinct 128-byte source cells, and every load
+      // instruction costs one L1 wavefront per distinct cell whatever its width -- the L1 data pipe, not DRAM,
+      // bounds this kernel (ncu: 80 % of peak with 128-bit loads), so half as many instructions for the same bytes
+      const float* src = fb + (size_t)cell[t] * C;
       const float w_t = wt[t];
 #pragma unroll
-      for (int q = 0; q < C / 4; ++q) {
-        const float4 v = __ldg(src + q);
-        acc[4 * q + 0] = fmaf(v.x, w_t, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(v.y, w_t, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(v.z, w_t, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(v.w, w_t, acc[4 * q + 3]);
+      for (int q = 0; q < C / 8; ++q) {
+        float v[8];
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(src + 8 * q));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[8 * q + i] = fmaf(v[i], w_t, acc[8 * q + i]);
       }
     }
   }
