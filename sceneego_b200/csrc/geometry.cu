@@ -491,29 +491,40 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
 // (4.2 MB of its 21 MB per frame).  One store per pixel into a plain grid plus this pass (1 MB read, 4.2 MB written,
 // every real cell: no clearing anywhere) is cheaper on both sides.  The grid is SELF-CLEANING: a block reads its rows
 // into shared memory, zeroes the entries that were set, and leaves the grid all-zero for the next batch.
-// One block = `rows` (x,y) rows of one frame, one thread per voxel.
+// One block = OE_K x `rows` (x,y) rows of one frame, one thread per OE_K voxels.
 // ---------------------------------------------------------------------------
+constexpr int OE_K = 4;       // row groups per thread: four loads in flight per thread (the pass is latency-, not bandwidth-bound)
 __global__ void __launch_bounds__(256) occ_expand_zwin_kernel(float* __restrict__ occ, __nv_bfloat16* __restrict__ vol,
                                                              sceneego_vol_layout_t lay, int plane, int V, int rows) {
-  extern __shared__ float s_row[];                       // rows x (V + 8): three zeros before, five after each row
+  extern __shared__ float s_row[];                       // OE_K x rows x (V + 8): three zeros before, five after each row
   const int z = threadIdx.x, r = threadIdx.y;
   const int b = blockIdx.y;
-  const int row = blockIdx.x * rows + r;                 // x * V + y
-  const bool in = row < V * V;
-  float* srow = s_row + r * (V + 8);
-  float v = 0.f;
-  float* src = occ + ((size_t)b * V * V + (in ? row : 0)) * V + z;
-  if (in) v = *src;
-  srow[z + 3] = v;
-  if (z < 3) srow[z] = 0.f;
-  if (z < 5) srow[V + 3 + z] = 0.f;
-  if (in && v != 0.f) *src = 0.f;
+  const int n_rows = V * V;
+  float v[OE_K];
+  int row[OE_K];
+#pragma unroll
+  for (int k = 0; k < OE_K; ++k) {
+    row[k] = (blockIdx.x * OE_K + k) * rows + r;         // x * V + y
+    v[k] = row[k] < n_rows ? occ[((size_t)b * n_rows + row[k]) * V + z] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < OE_K; ++k) {
+    float* srow = s_row + (k * rows + r) * (V + 8);
+    srow[z + 3] = v[k];
+    if (z < 3) srow[z] = 0.f;
+    if (z < 5) srow[V + 3 + z] = 0.f;
+    if (v[k] != 0.f) occ[((size_t)b * n_rows + row[k]) * V + z] = 0.f;
+  }
   __syncthreads();
-  if (!in) return;
-  const int x = row / V, y = row - x * V;
-  const uint4 cell = make_uint4(act_pack2(srow[z], srow[z + 1]), act_pack2(srow[z + 2], srow[z + 3]),
-                                act_pack2(srow[z + 4], srow[z + 5]), act_pack2(srow[z + 6], srow[z + 7]));
-  *reinterpret_cast<uint4*>(vol + ((int64_t)plane * lay.plane_stride + vol_pos(lay, b, x, y, z)) * 8) = cell;
+#pragma unroll
+  for (int k = 0; k < OE_K; ++k) {
+    if (row[k] >= n_rows) continue;
+    const float* srow = s_row + (k * rows + r) * (V + 8);
+    const int x = row[k] / V, y = row[k] - x * V;
+    const uint4 cell = make_uint4(act_pack2(srow[z], srow[z + 1]), act_pack2(srow[z + 2], srow[z + 3]),
+                                  act_pack2(srow[z + 4], srow[z + 5]), act_pack2(srow[z + 6], srow[z + 7]));
+    *reinterpret_cast<uint4*>(vol + ((int64_t)plane * lay.plane_stride + vol_pos(lay, b, x, y, z)) * 8) = cell;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -771,8 +782,8 @@ extern "C" int sceneego_occ_expand_zwin_bf16(float* d_occ_f32, void* d_vol, cons
   const int V = lay->side;
   SE_REQUIRE(V >= 8 && V <= 256, "occ_expand_zwin: side must be in [8, 256]");
   const int rows = 256 / V > 0 ? 256 / V : 1;
-  dim3 block((unsigned)V, (unsigned)rows), grid((unsigned)((V * V + rows - 1) / rows), (unsigned)batch);
-  occ_expand_zwin_kernel<<<grid, block, (size_t)rows * (V + 8) * sizeof(float), (cudaStream_t)stream>>>(
+  dim3 block((unsigned)V, (unsigned)rows), grid((unsigned)((V * V + rows * OE_K - 1) / (rows * OE_K)), (unsigned)batch);
+  occ_expand_zwin_kernel<<<grid, block, (size_t)OE_K * rows * (V + 8) * sizeof(float), (cudaStream_t)stream>>>(
       d_occ_f32, (__nv_bfloat16*)d_vol, *lay, channel / 8, V, rows);
   SE_CUDA_LAUNCH_CHECK("occ_expand_zwin");
   return SCENEEGO_OK;
