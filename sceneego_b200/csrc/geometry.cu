@@ -393,7 +393,9 @@ __device__ __forceinline__ void set_occupied(__nv_bfloat16* __restrict__ occ, co
   }
 }
 
-template <bool kPow2Side>
+// kPow2Side: 0 = divide by the cuboid side; 1 = the side is a power of two (x / 2^k == x * 2^-k exactly); 2 = the side AND
+// the volume size are powers of two: (x * V) * 2^-k == x * (V * 2^-k) exactly (both are exponent shifts), one multiply
+template <int kPow2Side>
 __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__ depth, int h, int w, NearestMaps nm,
                                                       const double* __restrict__ ray, int img_h, int img_w, int V,
                                                       double side, double inv_side, float* __restrict__ occ_f32,
@@ -454,10 +456,12 @@ __global__ void __launch_bounds__(256) voxelize_kernel(const float* __restrict__
     const bool zero = in_img && (dv == 0.0f);
     if (in_img && !zero) {
       const double d = (double)dv;
-      double qx = __dmul_rn(__dadd_rn(__dmul_rn(r0, d), half), Vd);
-      double qy = __dmul_rn(__dadd_rn(__dmul_rn(r1, d), half), Vd);
-      double qz = __dmul_rn(__dmul_rn(r2, d), Vd);
-      if (kPow2Side) {   // x / 2^k == x * 2^-k exactly (no fp64 divide on the hot path)
+      const double mul = kPow2Side == 2 ? __dmul_rn(Vd, inv_side) : Vd;     // exact: a power of two either way
+      double qx = __dmul_rn(__dadd_rn(__dmul_rn(r0, d), half), mul);
+      double qy = __dmul_rn(__dadd_rn(__dmul_rn(r1, d), half), mul);
+      double qz = __dmul_rn(__dmul_rn(r2, d), mul);
+      if (kPow2Side == 2) {
+      } else if (kPow2Side == 1) {   // x / 2^k == x * 2^-k exactly (no fp64 divide on the hot path)
         qx = __dmul_rn(qx, inv_side); qy = __dmul_rn(qy, inv_side); qz = __dmul_rn(qz, inv_side);
       } else {
         qx = __ddiv_rn(qx, side); qy = __ddiv_rn(qy, side); qz = __ddiv_rn(qz, side);
@@ -741,11 +745,15 @@ static int voxelize_impl(const float* d_depth, int batch, int h, int w, int pre_
   nm.pre_h = pre_h; nm.pre_w = pre_w; nm.clamp_max = clamp_max;
   int e2 = 0;
   const bool pow2 = side > 0 && frexp(side, &e2) == 0.5;       // side == 2^(e2-1): divide == exact multiply
-  if (pow2)
-    voxelize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 1.0 / side,
-                                                                  d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb, cols);
+  const bool pow2_v = V > 0 && (V & (V - 1)) == 0;
+  if (pow2 && pow2_v)
+    voxelize_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 1.0 / side,
+                                                               d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb, cols);
+  else if (pow2)
+    voxelize_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 1.0 / side,
+                                                               d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb, cols);
   else
-    voxelize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 0.0,
+    voxelize_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(d_depth, h, w, nm, d_ray, img_h, img_w, V, side, 0.0,
                                                                    d_occ_f32, (__nv_bfloat16*)d_occ_bf16, L, channel, batch, fpb, cols);
   SE_CUDA_LAUNCH_CHECK("voxelize");
   return SCENEEGO_OK;
